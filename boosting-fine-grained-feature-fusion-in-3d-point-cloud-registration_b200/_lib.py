@@ -1,0 +1,124 @@
+"""ctypes binding of ``libkpreg_b200.so`` (C ABI declared in ``include/kpreg_b200.h``).
+
+The product path has no CPU fallback: if the CUDA library is missing or a call is made without a
+CUDA device, this module raises.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkpreg_b200.so")
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_f32 = ctypes.c_float
+_c_ptr = ctypes.c_void_p
+_c_size = ctypes.c_size_t
+
+_SIGNATURES = {
+    "kpreg_version": (_c_int, []),
+    "kpreg_last_error": (ctypes.c_char_p, []),
+    "kpreg_launch_count": (ctypes.c_ulonglong, []),
+    "kpreg_subsample_workspace_bytes": (_c_int, [_c_i64, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_subsample_batch": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_int, _c_ptr, _c_ptr,
+                                       _c_ptr, _c_size, _c_ptr]),
+    "kpreg_grid_workspace_bytes": (_c_int, [_c_i64, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_grid_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_grid_query": (_c_int, [_c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_i64, _c_f32, _c_int, _c_int,
+                                  _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "kpreg_pack_rows": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_ptr]),
+    "kpreg_kpconv_workspace_bytes": (_c_int, [_c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int,
+                                              ctypes.POINTER(_c_size)]),
+    "kpreg_kpconv_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
+                                      _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_int, _c_ptr,
+                                      _c_ptr, _c_size, _c_ptr]),
+    "kpreg_kpconv_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64,
+                                       _c_i64, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_ptr,
+                                       _c_ptr, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_max_pool_forward": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr,
+                                        _c_ptr]),
+    "kpreg_max_pool_backward": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_int, _c_ptr, _c_ptr]),
+    "kpreg_kabsch": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f32, _c_int, _c_ptr, _c_ptr]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_ERRORS = {1: "invalid argument", 2: "workspace too small", 3: "CUDA error", 4: "grid too large to index"}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C <package>/csrc`.  kpreg_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    """Raise RuntimeError for a non-zero return code (the reference wrappers' error convention)."""
+    if rc != 0:
+        detail = _ERRORS.get(rc, f"error {rc}")
+        if rc == 3:
+            detail += ": " + load().kpreg_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what}: {detail}")
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: kpreg_b200 has no CPU path")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().kpreg_launch_count())
+
+
+class _Workspaces:
+    """One growing scratch buffer per (device, stream): kernels on a stream are ordered, so the
+    buffer can be reused call after call without extra synchronisation."""
+
+    def __init__(self) -> None:
+        self._bufs: Dict[Tuple[int, int], torch.Tensor] = {}
+
+    def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            # keep the old buffer alive until queued kernels are done: record it on the stream
+            if buf is not None:
+                buf.record_stream(torch.cuda.current_stream(device))
+            buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+workspaces = _Workspaces()
+
+
+def size_query(fn_name: str, *args) -> int:
+    out = _c_size(0)
+    check(getattr(load(), fn_name)(*args, ctypes.byref(out)), fn_name)
+    return int(out.value)

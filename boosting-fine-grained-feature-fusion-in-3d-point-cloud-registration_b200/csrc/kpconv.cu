@@ -1,0 +1,461 @@
+// Rigid KPConv forward / backward on sm_100a (CUDA-core parts).
+//
+// Replaces KPConv.forward() (reference models/backbone_kpconv/finegrained_kpconv_blocks.py:265-401):
+//   out[n,:] = (1/num[n]) * sum_k ( sum_h infl[n,h,k] * x[idx[n,h],:] ) @ W[k]
+//   infl     = clamp(1 - sqrt(|s[idx[n,h]] - q[n] - kp[k]|^2)/extent, 0)  (linear; :353-356)
+//   num[n]   = max(1, #{h : sum_c x[idx[n,h],c] > 0})                      (:396-399)
+// split into
+//   k_row_positive  : per support row, is its feature sum positive (the normalisation's predicate)
+//   k_kpconv_gather : one warp per query — lanes compute the K influences of 32 neighbours at a
+//                     time into shared memory, then every lane owns channels and streams the
+//                     gathered feature rows once, accumulating all K kernel points in registers;
+//                     writes the [n_q, K*c_in] aggregate (the gathered [n_q,H,c_in] tensor of the
+//                     reference is never materialised) and num[n]
+//   contraction     : [n_q, K*c_in] x [K*c_in, c_out] — tcgen05 kernel in kpconv_gemm.cu, or the
+//                     fp32 CUDA-core GEMM below (also used by the backward pass).
+// Shadow neighbours (index >= n_s; the reference's 1e6 point and zero feature row, :296/:375)
+// contribute exactly zero and are skipped.
+#include "common.cuh"
+
+namespace kpreg {
+
+int launch_kpconv_gemm_tc(const float* a, const float* w_split, const float* inv_num, float* out, int64_t m, int kd, int n,
+                          void* workspace, cudaStream_t stream);  // kpconv_gemm.cu
+int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, float* w_split, cudaStream_t stream);
+size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
+
+namespace {
+
+constexpr int KMAX = 16;             // kernel points handled per neighbour (reference ships 15)
+constexpr int kGatherWarps = 4;      // warps (= queries in flight) per CTA
+
+__global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ x, int64_t n_s, int c_in,
+                                                      unsigned char* __restrict__ pos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_s) return;
+  double acc = 0.0;
+  for (int c = lane; c < c_in; c += 32) acc += (double)x[row * c_in + c];
+  acc = warp_sum(acc);
+  if (lane == 0) pos[row] = (float)acc > 0.0f ? 1 : 0;
+}
+
+// Influence of the K kernel points on one neighbour (relative position rx,ry,rz).
+__device__ __forceinline__ void influences(float rx, float ry, float rz, const float* __restrict__ s_kp, int n_kpts,
+                                           float extent, int influence, int aggregation, float* __restrict__ w_out) {
+  float best = 3.4e38f;
+  int best_k = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float w = 0.f;
+    if (k < n_kpts) {
+      const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+      const float d2 = dx * dx + dy * dy + dz * dz;
+      if (influence == 1) w = fmaxf(1.0f - __fdiv_rn(sqrtf(d2), extent), 0.0f);
+      else if (influence == 2) { const float sig = extent * 0.3f; w = expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
+      else w = 1.0f;
+      if (d2 < best) { best = d2; best_k = k; }
+    }
+    w_out[k] = w;
+  }
+  if (aggregation == 1) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) if (k != best_k) w_out[k] = 0.f;
+  }
+}
+
+template <typename IdxT, int CPL>
+__global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
+    const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
+    const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
+    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num) {
+  __shared__ float s_kp[KMAX * 3];
+  __shared__ float s_w[kGatherWarps][32][KMAX + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
+  __syncthreads();
+
+  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+    const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
+    float acc[CPL][KMAX];
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) acc[cc][k] = 0.f;
+    int num = 0;
+
+    for (int h0 = 0; h0 < n_nbrs; h0 += 32) {
+      const int h = h0 + lane;
+      int64_t j = n_s;
+      if (h < n_nbrs) j = (int64_t)idx[n * n_nbrs + h];
+      const bool valid = j >= 0 && j < n_s;
+      if (valid) {
+        float w[KMAX];
+        influences(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, s_kp, n_kpts, extent, influence,
+                   aggregation, w);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) s_w[warp][lane][k] = w[k];
+      }
+      num += __popc(__ballot_sync(0xffffffffu, valid && row_pos[j] != 0));
+      const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+      __syncwarp();
+      const int lim = min(32, n_nbrs - h0);
+      for (int hh = 0; hh < lim; ++hh) {
+        if (!((vmask >> hh) & 1u)) continue;
+        const int64_t jj = __shfl_sync(0xffffffffu, j, hh);
+        const float* __restrict__ xr = x + jj * c_in;
+        float xv[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const int c = lane + 32 * cc;
+          xv[cc] = c < c_in ? xr[c] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const float wk = s_w[warp][hh][k];
+#pragma unroll
+          for (int cc = 0; cc < CPL; ++cc) acc[cc][k] = fmaf(wk, xv[cc], acc[cc][k]);
+        }
+      }
+      __syncwarp();
+    }
+    float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < n_kpts) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const int c = lane + 32 * cc;
+          if (c < c_in) arow[k * c_in + c] = acc[cc][k];
+        }
+      }
+    }
+    if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+  }
+}
+
+// d_x[idx[n,h], c] += sum_k infl[n,h,k] * d_agg[n,k,c]
+template <typename IdxT, int CPL>
+__global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
+    const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx,
+    const float* __restrict__ kernel_points, const float* __restrict__ d_agg, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
+    int c_in, float extent, int influence, int aggregation, float* __restrict__ d_x) {
+  __shared__ float s_kp[KMAX * 3];
+  __shared__ float s_w[kGatherWarps][32][KMAX + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+    const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
+    float da[CPL][KMAX];
+    const float* __restrict__ drow = d_agg + n * (int64_t)n_kpts * c_in;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+      for (int cc = 0; cc < CPL; ++cc) {
+        const int c = lane + 32 * cc;
+        da[cc][k] = (k < n_kpts && c < c_in) ? drow[k * c_in + c] : 0.f;
+      }
+    for (int h0 = 0; h0 < n_nbrs; h0 += 32) {
+      const int h = h0 + lane;
+      int64_t j = n_s;
+      if (h < n_nbrs) j = (int64_t)idx[n * n_nbrs + h];
+      const bool valid = j >= 0 && j < n_s;
+      if (valid) {
+        float w[KMAX];
+        influences(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, s_kp, n_kpts, extent, influence,
+                   aggregation, w);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) s_w[warp][lane][k] = w[k];
+      }
+      const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+      __syncwarp();
+      const int lim = min(32, n_nbrs - h0);
+      for (int hh = 0; hh < lim; ++hh) {
+        if (!((vmask >> hh) & 1u)) continue;
+        const int64_t jj = __shfl_sync(0xffffffffu, j, hh);
+        float v[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) v[cc] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const float wk = s_w[warp][hh][k];
+#pragma unroll
+          for (int cc = 0; cc < CPL; ++cc) v[cc] = fmaf(wk, da[cc][k], v[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const int c = lane + 32 * cc;
+          if (c < c_in) atomicAdd(d_x + jj * c_in + c, v[cc]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- fp32 CUDA-core GEMM: C[M,N] (+)= op(A)[M,Kd] * op(B)[Kd,N], optional per-row output scale ----
+//   TA: A is stored [Kd,M] (transposed).  TB: B is stored [N,Kd] (transposed).
+//   gridDim.z > 1 splits Kd; partial tiles are then combined with atomicAdd (C zeroed by the caller).
+constexpr int GM = 64, GN = 64, GK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_gemm_f32(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                  const float* __restrict__ row_scale, int64_t M, int N, int64_t Kd,
+                                                  int64_t k_per_split) {
+  __shared__ float sA[GK][GM + 4];
+  __shared__ float sB[GK][GN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GM;
+  const int n0 = blockIdx.y * GN;
+  const int64_t k_begin = (int64_t)blockIdx.z * k_per_split;
+  const int64_t k_end = min(Kd, k_begin + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += GK) {
+    // load A tile: GM x GK elements, 256 threads x 4
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = threadIdx.x + 256 * r;  // 0..1023
+      int mm, kk;
+      if (TA) { mm = e % GM; kk = e / GM; } else { kk = e % GK; mm = e / GK; }
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < k_end) v = TA ? A[gk * M + gm] : A[gm * Kd + gk];
+      sA[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      int nn, kk;
+      if (TB) { kk = e % GK; nn = e / GK; } else { nn = e % GN; kk = e / GN; }
+      const int gn = n0 + nn;
+      const int64_t gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < k_end) v = TB ? B[(int64_t)gn * Kd + gk] : B[gk * N + gn];
+      sB[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+    const float sc = row_scale ? row_scale[gm] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      if (gridDim.z > 1) atomicAdd(C + gm * N + gn, acc[i][j] * sc);
+      else C[gm * N + gn] = acc[i][j] * sc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scale_rows(const float* __restrict__ in, const float* __restrict__ scale, int64_t rows,
+                                                    int cols, float* __restrict__ out) {
+  const int64_t total = rows * (int64_t)cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * scale[i / cols];
+}
+
+template <bool TA, bool TB>
+int launch_gemm(const float* A, const float* B, float* C, const float* row_scale, int64_t M, int N, int64_t Kd, int splits,
+                cudaStream_t stream) {
+  if (M == 0 || N == 0) return KPREG_OK;
+  if (splits < 1) splits = 1;
+  int64_t per = (Kd + splits - 1) / splits;
+  per = (per + GK - 1) / GK * GK;
+  splits = (int)((Kd + per - 1) / per);
+  if (splits < 1) splits = 1;
+  if (splits > 1) KP_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
+  dim3 grid((unsigned)ceil_div(M, GM), (unsigned)ceil_div(N, GN), (unsigned)splits);
+  k_gemm_f32<TA, TB><<<grid, 256, 0, stream>>>(A, B, C, row_scale, M, N, Kd, per);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+struct KpconvWs {
+  unsigned char* row_pos; float* inv_num; float* agg; float* d_agg; float* g_scaled; float* w_split; void* gemm_ws; size_t total;
+};
+
+KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out, int backward) {
+  KpconvWs w;
+  Carver cv(base);
+  const size_t kd = (size_t)n_kpts * (size_t)c_in;
+  w.row_pos = cv.take<unsigned char>((size_t)n_s + 1);
+  w.inv_num = cv.take<float>((size_t)n_q + 1);
+  w.agg = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * kd);
+  w.d_agg = nullptr;
+  w.g_scaled = nullptr;
+  if (backward) {
+    w.d_agg = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * kd);
+    w.g_scaled = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * (size_t)c_out);
+  }
+  w.w_split = reinterpret_cast<float*>(cv.take<char>(kpconv_gemm_tc_weight_bytes((int)kd, c_out)));
+  w.gemm_ws = cv.take<char>(4096);
+  w.total = align_up(cv.used, 256);
+  return w;
+}
+
+template <typename IdxT>
+int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const float* x, const unsigned char* row_pos,
+                  const float* kp, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence,
+                  int aggregation, float* agg, float* inv_num, cudaStream_t stream) {
+  int blocks = ceil_div(n_q, kGatherWarps);
+  const int cap = kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  const IdxT* ip = static_cast<const IdxT*>(idx);
+#define KP_GATHER(CPL)                                                                                                     \
+  k_kpconv_gather<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, \
+                                                                       n_kpts, c_in, extent, influence, aggregation, agg,  \
+                                                                       inv_num)
+  if (c_in <= 32) KP_GATHER(1);
+  else if (c_in <= 64) KP_GATHER(2);
+  else if (c_in <= 128) KP_GATHER(4);
+  else if (c_in <= 256) KP_GATHER(8);
+  else return KPREG_E_INVALID;
+#undef KP_GATHER
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+template <typename IdxT>
+int launch_scatter(const float* q_pts, const float* s_pts, const void* idx, const float* kp, const float* d_agg, int64_t n_q,
+                   int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence, int aggregation, float* d_x,
+                   cudaStream_t stream) {
+  int blocks = ceil_div(n_q, kGatherWarps);
+  const int cap = kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  const IdxT* ip = static_cast<const IdxT*>(idx);
+#define KP_SCATTER(CPL)                                                                                                  \
+  k_kpconv_scatter<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, kp, d_agg, n_q, n_s, n_nbrs,   \
+                                                                        n_kpts, c_in, extent, influence, aggregation, d_x)
+  if (c_in <= 32) KP_SCATTER(1);
+  else if (c_in <= 64) KP_SCATTER(2);
+  else if (c_in <= 128) KP_SCATTER(4);
+  else if (c_in <= 256) KP_SCATTER(8);
+  else return KPREG_E_INVALID;
+#undef KP_SCATTER
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+int check_kpconv_args(int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out, float extent, int influence,
+                      int aggregation) {
+  if (n_q < 0 || n_s < 0 || n_nbrs < 0 || n_kpts < 1 || n_kpts > KMAX || c_in < 1 || c_in > 256 || c_out < 1) return KPREG_E_INVALID;
+  if (!(extent > 0.f) || influence < 0 || influence > 2 || aggregation < 0 || aggregation > 1) return KPREG_E_INVALID;
+  return KPREG_OK;
+}
+
+}  // namespace
+}  // namespace kpreg
+
+using namespace kpreg;
+
+extern "C" int kpreg_kpconv_workspace_bytes(int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out, int backward,
+                                            size_t* bytes) {
+  if (!bytes || n_q < 0 || n_s < 0 || n_kpts < 1 || c_in < 1 || c_out < 1) return KPREG_E_INVALID;
+  *bytes = carve_kpconv(nullptr, n_q, n_s, n_kpts, c_in, c_out, backward).total;
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, const void* idx, int idx64, const float* x,
+                                    const float* weights, const float* kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
+                                    int n_kpts, int c_in, int c_out, float kp_extent, int influence, int aggregation, int gemm,
+                                    float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  int rc = check_kpconv_args(n_q, n_s, n_nbrs, n_kpts, c_in, c_out, kp_extent, influence, aggregation);
+  if (rc) return rc;
+  if (n_q == 0) return KPREG_OK;
+  if (!q_pts || !weights || !kernel_points || !out || !workspace) return KPREG_E_INVALID;
+  if (n_s > 0 && (!s_pts || !x)) return KPREG_E_INVALID;
+  if (n_nbrs > 0 && !idx) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 0);
+  if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
+  if (n_s > 0) {
+    k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, w.row_pos);
+    KP_LAUNCH_CHECK();
+  }
+  rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                      influence, aggregation, w.agg, w.inv_num, stream)
+             : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                      influence, aggregation, w.agg, w.inv_num, stream);
+  if (rc) return rc;
+  const int kd = n_kpts * c_in;
+  if (gemm == 1) {
+    rc = kpconv_gemm_tc_prepare_weights(weights, kd, c_out, w.w_split, stream);
+    if (rc) return rc;
+    return launch_kpconv_gemm_tc(w.agg, w.w_split, w.inv_num, out, n_q, kd, c_out, w.gemm_ws, stream);
+  }
+  return launch_gemm<false, false>(w.agg, weights, out, w.inv_num, n_q, c_out, kd, 1, stream);
+}
+
+extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, const void* idx, int idx64, const float* x,
+                                     const float* weights, const float* kernel_points, const float* grad_out, int64_t n_q,
+                                     int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out, float kp_extent, int influence,
+                                     int aggregation, float* d_x, float* d_weights, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
+  int rc = check_kpconv_args(n_q, n_s, n_nbrs, n_kpts, c_in, c_out, kp_extent, influence, aggregation);
+  if (rc) return rc;
+  if (!d_weights || !weights || !kernel_points || !workspace) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int kd = n_kpts * c_in;
+  KP_CUDA_TRY(cudaMemsetAsync(d_weights, 0, sizeof(float) * (size_t)kd * (size_t)c_out, stream));
+  if (n_s > 0) {
+    if (!d_x) return KPREG_E_INVALID;
+    KP_CUDA_TRY(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)n_s * (size_t)c_in, stream));
+  }
+  if (n_q == 0 || n_s == 0) return KPREG_OK;
+  if (!q_pts || !s_pts || !x || !grad_out || (n_nbrs > 0 && !idx)) return KPREG_E_INVALID;
+  KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 1);
+  if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
+  // recompute the aggregate and the normalisation (cheaper than keeping [n_q, K*c_in] alive per layer)
+  k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, w.row_pos);
+  KP_LAUNCH_CHECK();
+  rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                      influence, aggregation, w.agg, w.inv_num, stream)
+             : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                      influence, aggregation, w.agg, w.inv_num, stream);
+  if (rc) return rc;
+  // g' = grad_out / num
+  {
+    int blocks = ceil_div(n_q * (int64_t)c_out, 256);
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    k_scale_rows<<<blocks, 256, 0, stream>>>(grad_out, w.inv_num, n_q, c_out, w.g_scaled);
+    KP_LAUNCH_CHECK();
+  }
+  // d_weights[K*c_in, c_out] = agg^T g'   (reduction over the queries, split across CTAs)
+  {
+    const int tiles = ceil_div(kd, GM) * ceil_div(c_out, GN);
+    int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    const int max_splits = ceil_div(n_q, 4 * GK);
+    if (splits > max_splits) splits = max_splits;
+    rc = launch_gemm<true, false>(w.agg, w.g_scaled, d_weights, nullptr, kd, c_out, n_q, splits, stream);
+    if (rc) return rc;
+  }
+  // d_agg[n_q, K*c_in] = g' W^T
+  rc = launch_gemm<false, true>(w.g_scaled, weights, w.d_agg, nullptr, n_q, kd, c_out, 1, stream);
+  if (rc) return rc;
+  return idx64 ? launch_scatter<int64_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                         influence, aggregation, d_x, stream)
+               : launch_scatter<int32_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                         influence, aggregation, d_x, stream);
+}

@@ -1,0 +1,432 @@
+// Radius neighbours of a stacked batch on sm_100a: uniform-grid cell binning + warp-per-query sweep.
+//
+// Replaces batch_nanoflann_neighbors() (reference cpp_neighbors/neighbors/neighbors.cpp:211-332).
+// The reference's KD-tree is only an accelerator; what defines the result is
+//   - the metric   d2 = (dx*dx + dy*dy) + dz*dz in fp32 without FMA   (nanoflann.hpp:432-440)
+//   - the test     d2 < r*r, strict                                    (nanoflann.hpp:249-253)
+//   - the order    ascending d2 (nanoflann.hpp:1280-1289); ties by index here
+//   - the row      local index + cloud offset, padded with n_supports (neighbors.cpp:304-327)
+// and those are reproduced bit for bit.
+//
+// Grid build (once per support set):
+//   cell key = cloud<<42 | cz<<28 | cy<<14 | cx, coordinates relative to the batch bounding box,
+//   computed in fp64 so that a neighbour within r can never be more than one cell away;
+//   supports are radix-sorted by key into a float4 array (xyz + local index); every occupied cell
+//   gets a [start,end) range in an open-addressing hash table (64-bit keys, linear probing).
+// Query (one warp per query point):
+//   lanes 0..26 look up the 27 surrounding cells; the warp then walks the concatenated ranges 32
+//   candidates at a time (coalesced 16-byte loads), compacts the hits with a ballot into shared
+//   memory as 64-bit (d2 bits << 32 | index) keys, ranks them by counting and writes the row with
+//   coalesced (vectorised when the width allows) stores.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace kpreg {
+namespace {
+
+constexpr int kCellBits = 14;
+constexpr int kCellMax = (1 << kCellBits) - 1;
+constexpr int kCloudShift = 3 * kCellBits;
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr int kWarpsPerBlock = 8;
+constexpr int kHitCap = 256;  // hits buffered per query in shared memory; beyond: recount path
+
+struct GridHeader {  // lives at the start of the grid workspace (device memory)
+  double min[3];
+  double inv_cell;
+  int32_t dims[3];
+  int32_t status;
+};
+
+struct GridWs {
+  GridHeader* hdr; int64_t* off; int64_t* q_off; unsigned int* bbox;
+  uint64_t* keys0; uint64_t* keys1; uint32_t* idx0; uint32_t* idx1;
+  float4* sorted; uint64_t* tab_key; int2* tab_val;
+  void* cub_tmp; size_t cub_tmp_bytes; uint32_t tab_cap; size_t total;
+  int64_t n; int n_clouds;
+};
+
+GridWs carve_grid(void* base, int64_t n, int n_clouds) {
+  GridWs w;
+  Carver cv(base);
+  const size_t np = (size_t)(n > 0 ? n : 1);
+  w.hdr = cv.take<GridHeader>(1);
+  w.off = cv.take<int64_t>((size_t)n_clouds + 1);
+  w.q_off = cv.take<int64_t>((size_t)n_clouds + 1);
+  w.bbox = cv.take<unsigned int>(8);
+  w.keys0 = cv.take<uint64_t>(np);
+  w.keys1 = cv.take<uint64_t>(np);
+  w.idx0 = cv.take<uint32_t>(np);
+  w.idx1 = cv.take<uint32_t>(np);
+  w.sorted = cv.take<float4>(np);
+  uint32_t cap = 64;
+  while ((size_t)cap < 2 * np) cap <<= 1;
+  w.tab_cap = cap;
+  w.tab_key = cv.take<uint64_t>(cap);
+  w.tab_val = cv.take<int2>(cap);
+  w.cub_tmp_bytes = (size_t)(8u << 20) + np * 16;
+  w.cub_tmp = cv.take<char>(w.cub_tmp_bytes);
+  w.total = align_up(cv.used, 256);
+  w.n = n;
+  w.n_clouds = n_clouds;
+  return w;
+}
+
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+__global__ void k_grid_init(unsigned int* __restrict__ bbox, GridHeader* __restrict__ hdr) {
+  if (threadIdx.x < 6) bbox[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+  if (threadIdx.x == 0) hdr->status = 0;
+}
+
+__global__ void __launch_bounds__(256) k_grid_bbox(const float* __restrict__ pts, int64_t n, unsigned int* __restrict__ bbox) {
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float v = pts[3 * i + d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  }
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(bbox + d, float_to_ordered(mn[d]));
+      atomicMax(bbox + 3 + d, float_to_ordered(mx[d]));
+    }
+  }
+}
+
+// The cell edge is `cell` widened by 1e-6 (fp32 rounding of d2 and r*r can never admit a point that
+// is a full widened cell away), and widened further if the batch extent would overflow 14 bits/axis.
+__global__ void k_grid_header(const unsigned int* __restrict__ bbox, float cell, GridHeader* __restrict__ hdr) {
+  if (threadIdx.x != 0) return;
+  double edge = (double)cell * (1.0 + 1e-6);
+  double ext = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    double mn = (double)ordered_to_float(bbox[d]);
+    double mx = (double)ordered_to_float(bbox[3 + d]);
+    hdr->min[d] = mn;
+    ext = fmax(ext, mx - mn);
+  }
+  if (!(ext / edge < (double)(kCellMax - 1))) edge = ext / (double)(kCellMax - 2);
+  if (!(edge > 0.0) || !isfinite(edge)) { edge = 1.0; hdr->status = KPREG_E_RANGE; }
+  hdr->inv_cell = 1.0 / edge;
+  for (int d = 0; d < 3; ++d) {
+    double mx = (double)ordered_to_float(bbox[3 + d]);
+    hdr->dims[d] = (int)floor((mx - hdr->min[d]) * hdr->inv_cell) + 1;
+  }
+}
+
+__device__ __forceinline__ void cell_coords(const GridHeader& h, float x, float y, float z, int& cx, int& cy, int& cz) {
+  cx = (int)floor(((double)x - h.min[0]) * h.inv_cell);
+  cy = (int)floor(((double)y - h.min[1]) * h.inv_cell);
+  cz = (int)floor(((double)z - h.min[2]) * h.inv_cell);
+}
+
+__device__ __forceinline__ uint64_t make_key(int cloud, int cx, int cy, int cz) {
+  return ((uint64_t)cloud << kCloudShift) | ((uint64_t)cz << (2 * kCellBits)) | ((uint64_t)cy << kCellBits) | (uint64_t)cx;
+}
+
+__global__ void __launch_bounds__(256) k_cell_keys(const float* __restrict__ pts, const int64_t* __restrict__ off, int n_clouds,
+                                                   int64_t n, const GridHeader* __restrict__ hdr, uint64_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GridHeader h = *hdr;
+  int c = cloud_of(off, n_clouds, i);
+  int cx, cy, cz;
+  cell_coords(h, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], cx, cy, cz);
+  cx = min(max(cx, 0), kCellMax);
+  cy = min(max(cy, 0), kCellMax);
+  cz = min(max(cz, 0), kCellMax);
+  keys[i] = make_key(c, cx, cy, cz);
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_table_clear(uint64_t* __restrict__ tab_key, uint32_t cap) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) tab_key[i] = kEmptyKey;
+}
+
+// Gather the sorted float4 array (xyz + LOCAL index bits) and register every cell in the hash table.
+__global__ void __launch_bounds__(256) k_grid_fill(const float* __restrict__ pts, const int64_t* __restrict__ off,
+                                                   const uint64_t* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted,
+                                                   int64_t n, float4* __restrict__ sorted, uint64_t* __restrict__ tab_key,
+                                                   int2* __restrict__ tab_val, uint32_t cap) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint64_t key = keys_sorted[p];
+  const uint32_t i = idx_sorted[p];
+  const int cloud = (int)(key >> kCloudShift);
+  sorted[p] = make_float4(pts[3 * (int64_t)i], pts[3 * (int64_t)i + 1], pts[3 * (int64_t)i + 2],
+                          __int_as_float((int)((int64_t)i - off[cloud])));
+  if (p > 0 && keys_sorted[p - 1] == key) return;
+  int64_t e = p + 1;
+  while (e < n && keys_sorted[e] == key) ++e;
+  uint32_t slot = hash_key(key) & (cap - 1);
+  while (true) {
+    unsigned long long prev = atomicCAS((unsigned long long*)&tab_key[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey) { tab_val[slot] = make_int2((int)p, (int)e); break; }
+    slot = (slot + 1) & (cap - 1);
+  }
+}
+
+__device__ __forceinline__ int2 table_find(const uint64_t* __restrict__ tab_key, const int2* __restrict__ tab_val, uint32_t cap,
+                                           uint64_t key) {
+  uint32_t slot = hash_key(key) & (cap - 1);
+  while (true) {
+    const uint64_t k = tab_key[slot];
+    if (k == key) return tab_val[slot];
+    if (k == kEmptyKey) return make_int2(0, 0);
+    slot = (slot + 1) & (cap - 1);
+  }
+}
+
+__device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float sx, float sy, float sz) {
+  // nanoflann L2_Simple_Adaptor::evalMetric: result = 0; result += diff*diff for x, y, z — no FMA.
+  const float dx = __fsub_rn(qx, sx), dy = __fsub_rn(qy, sy), dz = __fsub_rn(qz, sz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
+    const GridHeader* __restrict__ hdr, const int64_t* __restrict__ s_off, int n_clouds, int64_t n_supports,
+    const float4* __restrict__ sorted, const uint64_t* __restrict__ tab_key, const int2* __restrict__ tab_val, uint32_t cap,
+    const float* __restrict__ queries, const int64_t* __restrict__ q_off, int64_t n_queries, float radius, float r2, int width,
+    OutT* __restrict__ out, int32_t* __restrict__ out_counts, int32_t* __restrict__ out_stats) {
+  __shared__ unsigned long long s_hits[kWarpsPerBlock][kHitCap];
+  __shared__ int s_cell_start[kWarpsPerBlock][32];
+  __shared__ int s_cell_prefix[kWarpsPerBlock][32];
+  __shared__ int s_block_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_block_max = 0;
+  __syncthreads();
+  const GridHeader h = *hdr;
+  int my_max = 0;
+  unsigned long long* hits = s_hits[warp];
+
+  for (int64_t qi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; qi < n_queries; qi += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
+    const int cloud = cloud_of(q_off, n_clouds, qi);
+    const int64_t cloud_base = s_off[cloud];
+    int cx, cy, cz;
+    cell_coords(h, qx, qy, qz, cx, cy, cz);
+    cx = min(max(cx, -2), kCellMax + 2);
+    cy = min(max(cy, -2), kCellMax + 2);
+    cz = min(max(cz, -2), kCellMax + 2);
+    // lanes 0..26: one surrounding cell each
+    int start = 0, len = 0;
+    if (lane < 27) {
+      const int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
+      if (nx >= 0 && ny >= 0 && nz >= 0 && nx < h.dims[0] && ny < h.dims[1] && nz < h.dims[2]) {
+        const int2 rng = table_find(tab_key, tab_val, cap, make_key(cloud, nx, ny, nz));
+        start = rng.x;
+        len = rng.y - rng.x;
+      }
+    }
+    const int incl = warp_scan_inclusive(len);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    s_cell_start[warp][lane] = start;
+    s_cell_prefix[warp][lane] = incl - len;  // exclusive prefix
+    __syncwarp();
+
+    int count = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      unsigned long long packed = 0ull;
+      if (t < total) {
+        // last cell whose exclusive prefix is <= t (prefixes are non-decreasing; empty cells repeat)
+        int lo = 0, hi = 27;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_cell_prefix[warp][mid] <= t) lo = mid; else hi = mid;
+        }
+        const float4 sp = sorted[s_cell_start[warp][lo] + (t - s_cell_prefix[warp][lo])];
+        const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+        hit = d2 < r2;
+        packed = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+      }
+      const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (pos < kHitCap) hits[pos] = packed;
+      }
+      count += __popc(mask);
+    }
+    __syncwarp();
+    OutT* row = out + qi * (int64_t)width;
+    if (count <= kHitCap) {
+      // rank by counting: keys are distinct (distinct indices), so rank = number of smaller keys
+      for (int e = lane; e < count; e += 32) {
+        const unsigned long long mine = hits[e];
+        int rank = 0;
+        for (int j = 0; j < count; ++j) rank += (hits[j] < mine) ? 1 : 0;
+        if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
+      }
+    } else {
+      // more hits than the shared buffer holds: recount from the candidate ranges (rare, exact, slow)
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool hit = false;
+        unsigned long long mine = 0ull;
+        if (t < total) {
+          int lo = 0, hi = 27;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_cell_prefix[warp][mid] <= t) lo = mid; else hi = mid;
+          }
+          const float4 sp = sorted[s_cell_start[warp][lo] + (t - s_cell_prefix[warp][lo])];
+          const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+          hit = d2 < r2;
+          mine = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+        }
+        if (hit) {
+          int rank = 0;
+          for (int cidx = 0; cidx < 27; ++cidx) {
+            const int cs = s_cell_start[warp][cidx];
+            const int ce = cs + ((cidx < 26 ? s_cell_prefix[warp][cidx + 1] : total) - s_cell_prefix[warp][cidx]);
+            for (int j = cs; j < ce; ++j) {
+              const float4 o = sorted[j];
+              const float od2 = dist2_ref(qx, qy, qz, o.x, o.y, o.z);
+              const unsigned long long ok = ((unsigned long long)__float_as_uint(od2) << 32) | (unsigned int)__float_as_int(o.w);
+              rank += (od2 < r2 && ok < mine) ? 1 : 0;
+            }
+          }
+          if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
+        }
+      }
+    }
+    for (int e = count + lane; e < width; e += 32) row[e] = (OutT)n_supports;
+    if (out_counts != nullptr && lane == 0) out_counts[qi] = count;
+    my_max = max(my_max, count);
+    __syncwarp();
+  }
+  if (lane == 0 && my_max > 0) atomicMax(&s_block_max, my_max);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_block_max > 0) atomicMax(out_stats, s_block_max);
+    if (h.status != 0) atomicMax(out_stats + 1, h.status);
+    // the 27-cell sweep is only exhaustive while the query radius does not exceed the cell edge
+    if ((double)radius * (1.0 + 5e-7) * h.inv_cell > 1.0) atomicMax(out_stats + 1, (int32_t)KPREG_E_RANGE);
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_pack_rows(const int32_t* __restrict__ in, int64_t n_rows, int in_width, int out_width,
+                                                   OutT* __restrict__ out) {
+  const int64_t total = n_rows * (int64_t)out_width;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / out_width;
+    const int cidx = (int)(i - r * out_width);
+    out[i] = (OutT)in[r * (int64_t)in_width + cidx];
+  }
+}
+
+}  // namespace
+}  // namespace kpreg
+
+using namespace kpreg;
+
+extern "C" int kpreg_grid_workspace_bytes(int64_t n_supports, int n_clouds, size_t* bytes) {
+  if (!bytes || n_supports < 0 || n_clouds < 0) return KPREG_E_INVALID;
+  *bytes = carve_grid(nullptr, n_supports, n_clouds).total;
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_grid_build(const float* supports, const int32_t* s_lens, int64_t n, int n_clouds, float cell,
+                                void* grid, size_t grid_bytes, void* stream_) {
+  if (!s_lens || !grid || n < 0 || n_clouds < 1 || !(cell > 0.f)) return KPREG_E_INVALID;
+  if (n > 0 && !supports) return KPREG_E_INVALID;
+  if (n >= (int64_t)0x7fffffff || n_clouds >= (1 << (63 - kCloudShift))) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GridWs w = carve_grid(grid, n, n_clouds);
+  if (w.total > grid_bytes) return KPREG_E_WORKSPACE;
+  int rc = launch_cloud_offsets(s_lens, n_clouds, w.off, stream);
+  if (rc) return rc;
+  k_grid_init<<<1, 32, 0, stream>>>(w.bbox, w.hdr);
+  KP_LAUNCH_CHECK();
+  const int blocks = n > 0 ? ceil_div(n, 256) : 1;
+  if (n > 0) {
+    k_grid_bbox<<<blocks < 4 * kNumSMs ? blocks : 4 * kNumSMs, 256, 0, stream>>>(supports, n, w.bbox);
+    KP_LAUNCH_CHECK();
+  }
+  k_grid_header<<<1, 32, 0, stream>>>(w.bbox, cell, w.hdr);
+  KP_LAUNCH_CHECK();
+  k_table_clear<<<ceil_div(w.tab_cap, 1024) < 8 * kNumSMs ? ceil_div(w.tab_cap, 1024) : 8 * kNumSMs, 256, 0, stream>>>(w.tab_key, w.tab_cap);
+  KP_LAUNCH_CHECK();
+  if (n == 0) return KPREG_OK;
+  k_cell_keys<<<blocks, 256, 0, stream>>>(supports, w.off, n_clouds, n, w.hdr, w.keys0, w.idx0);
+  KP_LAUNCH_CHECK();
+  cub::DoubleBuffer<uint64_t> dk(w.keys0, w.keys1);
+  cub::DoubleBuffer<uint32_t> dv(w.idx0, w.idx1);
+  const int end_bit = kCloudShift + bits_for((uint64_t)n_clouds);
+  size_t need = 0;
+  KP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, 0, end_bit, stream));
+  if (need > w.cub_tmp_bytes) return KPREG_E_WORKSPACE;
+  KP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, need, dk, dv, (int)n, 0, end_bit, stream));
+  count_launches((unsigned long long)(2 + (end_bit + 7) / 8));
+  k_grid_fill<<<blocks, 256, 0, stream>>>(supports, w.off, dk.Current(), dv.Current(), n, w.sorted, w.tab_key, w.tab_val, w.tab_cap);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const float* queries, const int32_t* q_lens,
+                                int64_t n_queries, float radius, int width, int idx64, void* out_idx, int32_t* out_counts,
+                                int32_t* out_stats, void* stream_) {
+  if (!grid || !q_lens || !out_stats || n < 0 || n_clouds < 1 || n_queries < 0 || width < 0 || !(radius > 0.f)) return KPREG_E_INVALID;
+  if (n_queries == 0) return KPREG_OK;
+  if (!queries || (width > 0 && !out_idx)) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GridWs w = carve_grid(const_cast<void*>(grid), n, n_clouds);
+  int64_t* q_off = w.q_off;
+  int rc = launch_cloud_offsets(q_lens, n_clouds, q_off, stream);
+  if (rc) return rc;
+  const float r2 = radius * radius;  // neighbors.cpp:226, fp32
+  int blocks = ceil_div(n_queries, kWarpsPerBlock);
+  const int max_blocks = kNumSMs * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (idx64) {
+    k_grid_query<int64_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
+                                                                     w.tab_cap, queries, q_off, n_queries, radius, r2, width,
+                                                                     static_cast<int64_t*>(out_idx), out_counts, out_stats);
+  } else {
+    k_grid_query<int32_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
+                                                                     w.tab_cap, queries, q_off, n_queries, radius, r2, width,
+                                                                     static_cast<int32_t*>(out_idx), out_counts, out_stats);
+  }
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_pack_rows(const int32_t* in, int64_t n_rows, int in_width, int out_width, int idx64, void* out,
+                               void* stream_) {
+  if (n_rows < 0 || in_width < 0 || out_width < 0 || out_width > in_width) return KPREG_E_INVALID;
+  if (n_rows == 0 || out_width == 0) return KPREG_OK;
+  if (!in || !out) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t total = n_rows * (int64_t)out_width;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  if (idx64) k_pack_rows<int64_t><<<blocks, 256, 0, stream>>>(in, n_rows, in_width, out_width, static_cast<int64_t*>(out));
+  else k_pack_rows<int32_t><<<blocks, 256, 0, stream>>>(in, n_rows, in_width, out_width, static_cast<int32_t*>(out));
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}

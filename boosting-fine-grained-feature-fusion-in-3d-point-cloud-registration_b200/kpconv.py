@@ -1,0 +1,233 @@
+"""KPConv pyramid construction and encoder — host-side mirror of the reference's
+``models/backbone_kpconv/finegrained_kpconv.py`` on top of the CUDA operators.
+
+Drop-in surface (same names, arguments, result layout):
+
+* ``batch_grid_subsampling_kpconv`` (reference :175-215) and ``batch_neighbors_kpconv`` (:248-263);
+* ``Preprocessor(cfg)(pts) -> {'points','neighbors','pools','upsamples','stack_lengths'}`` (:296-419):
+  index tensors int64 padded with the support level's row count, row width ``min(max_count, limit)``,
+  empty ``(0,1)`` / ``(0,3)`` placeholders at the last level.  The results are those of the reference's
+  deterministic CPU ``Preprocessor`` (not of its order-nondeterministic ``PreprocessorGPU``, :422-542),
+  bit for bit, but computed on the device: the whole pyramid is enqueued with one small host read-back
+  per subsampled level (its point count decides the next level's launch sizes) and one at the end (the
+  row widths), instead of the reference's device->host->device round trip of every table;
+* ``KPFEncoder(config, d_bottle, increase_channel_when_downsample=True)(x, batch) -> (x, skip_x)`` (:22-95).
+"""
+from __future__ import annotations
+
+import logging
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .cpp_wrappers import cpp_neighbors, cpp_subsampling
+from .kpconv_blocks import block_decider
+
+_logger = logging.getLogger(__name__)
+
+
+def batch_grid_subsampling_kpconv(points, batches_len, features=None, labels=None, sampleDl=0.1, max_p=0, verbose=0,
+                                  random_grid_orient=True):
+    """Grid subsampling of a stacked batch -> (s_points, s_len) tensors on the device of ``points``."""
+    if features is not None or labels is not None:
+        raise NotImplementedError("batch_grid_subsampling_kpconv: features / labels are not used by the registration path")
+    s_points, s_len = cpp_subsampling.subsample_batch(points, batches_len, sampleDl=sampleDl, max_p=max_p,
+                                                      verbose=verbose)
+    if isinstance(s_points, np.ndarray):
+        return torch.from_numpy(s_points), torch.from_numpy(s_len)
+    return s_points, s_len
+
+
+def batch_neighbors_kpconv(queries, supports, q_batches, s_batches, radius, max_neighbors):
+    """Radius neighbours of a stacked batch, truncated to the ``max_neighbors`` closest when > 0."""
+    neighbors = cpp_neighbors.batch_query(queries, supports, q_batches, s_batches, radius=radius)
+    if isinstance(neighbors, np.ndarray):
+        neighbors = torch.from_numpy(neighbors)
+    return neighbors[:, :max_neighbors] if max_neighbors > 0 else neighbors
+
+
+class _Table:
+    """A neighbour table still in its over-allocated [Nq, limit] int32 form, awaiting its row width."""
+    __slots__ = ("rows", "limit", "slot")
+
+    def __init__(self, rows, limit, slot):
+        self.rows, self.limit, self.slot = rows, limit, slot
+
+
+class Preprocessor(nn.Module):
+    """Computes the metadata used for KPConv (pyramid points, neighbour / pool / upsample tables)."""
+
+    def __init__(self, cfg, index_dtype: torch.dtype = torch.int64):
+        super().__init__()
+        self.cfg = cfg
+        self.index_dtype = index_dtype
+
+    @torch.no_grad()
+    def forward(self, pts: List[torch.Tensor]):
+        cfg = self.cfg
+        limits = cfg.neighborhood_limits
+        arch = list(cfg.architecture)
+        in_device = pts[0].device
+        dev = in_device if in_device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+
+        lens_host = [int(p.shape[0]) for p in pts]
+        points = torch.cat([p.to(torch.float32) for p in pts], dim=0)
+        if not points.is_cuda:
+            points = points.pin_memory().to(dev, non_blocking=True)
+        lens = torch.tensor(lens_host, dtype=torch.int32).to(dev, non_blocking=True)
+        n_clouds = len(lens_host)
+
+        # every table's {max count, status} pair lands in one stats tensor, read once at the end
+        n_tables_max = 3 * len(arch) + 3
+        stats = torch.zeros((n_tables_max, 2), dtype=torch.int32, device=dev)
+        next_slot = [0]
+
+        def query(grid, q_pts, q_lens, radius, limit):
+            slot = next_slot[0]
+            next_slot[0] += 1
+            if limit > 0:
+                rows, _, _ = grid.query(q_pts, q_lens, radius, limit, stats=stats[slot])
+                return _Table(rows, limit, slot)
+            # no limit: the width itself is data dependent -> count first (one extra read-back)
+            _, _, st = grid.query(q_pts, q_lens, radius, 0, stats=stats[slot])
+            width = int(st[0].item())
+            rows, _, _ = grid.query(q_pts, q_lens, radius, max(width, 1), stats=stats[slot])
+            return _Table(rows, max(width, 1), slot)
+
+        r_normal = cfg.first_subsampling_dl * cfg.conv_radius
+        level_points, level_lens = [], []
+        conv_tabs, pool_tabs, up_tabs = [], [], []
+        layer_blocks, layer = [], 0
+        pending_up = None  # (fine points, fine lens, radius, limit): answered by the next level's grid
+
+        for block_i, block in enumerate(arch):
+            if 'global' in block or 'upsample' in block:
+                break
+            strided = 'pool' in block or 'strided' in block
+            if not strided:
+                layer_blocks.append(block)
+                if block_i < len(arch) - 1 and 'upsample' not in arch[block_i + 1]:
+                    continue
+
+            deform_conv = any('deformable' in b for b in layer_blocks[:-1])
+            r_conv = r_normal * cfg.deform_radius / cfg.conv_radius if deform_conv else r_normal
+            r_pool = r_normal * cfg.deform_radius / cfg.conv_radius if 'deformable' in block else r_normal
+            # one cell grid per level serves the conv table, the pool table (coarse queries) and the previous
+            # level's upsample table (fine queries, radius 2*r_prev = r of this level)
+            cell = max(r_conv if layer_blocks else 0.0, r_pool if strided else 0.0,
+                       pending_up[2] if pending_up is not None else 0.0)
+            grid = ops.CellGrid(points, lens, cell) if cell > 0 else None
+
+            if pending_up is not None:
+                up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3]))
+                pending_up = None
+            conv_tabs.append(query(grid, points, lens, r_conv, limits[layer]) if layer_blocks else None)
+
+            level_points.append(points)
+            level_lens.append(lens)
+            if strided:
+                dl = 2 * r_normal / cfg.conv_radius
+                sub, counts = ops.subsample(points, lens, dl)
+                host = counts.cpu()  # sizes of the next level: the one unavoidable read-back per level
+                if int(host[-1]) != 0:
+                    raise RuntimeError("Preprocessor: voxel grid too large to index")
+                m = int(host[-2])
+                if m < 1:
+                    raise RuntimeError("Error")
+                pool_p, pool_b = sub[:m], counts[:n_clouds]
+                pool_tabs.append(query(grid, pool_p, pool_b, r_pool, limits[layer]))
+                pending_up = (points, lens, 2 * r_pool, limits[layer])
+                points, lens = pool_p, pool_b
+            else:
+                pool_tabs.append(None)
+                up_tabs.append(None)
+            r_normal *= 2
+            layer += 1
+            layer_blocks = []
+
+        if pending_up is not None:
+            # architecture ended on a strided block: the upsample table still needs the coarse grid
+            grid = ops.CellGrid(points, lens, pending_up[2])
+            up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3]))
+            pending_up = None
+            level_points.append(points)
+            level_lens.append(lens)
+            conv_tabs.append(None)
+            pool_tabs.append(None)
+            up_tabs.append(None)
+
+        host_stats = stats.cpu()
+        if int(host_stats[:, 1].max()) != 0:
+            raise RuntimeError("Preprocessor: cell grid too large to index")
+        idx64 = self.index_dtype == torch.int64
+
+        def finish(tab):
+            if tab is None:
+                return torch.zeros((0, 1), dtype=torch.int64, device=dev)
+            width = min(int(host_stats[tab.slot, 0]), tab.limit)
+            if tab.rows.shape[0] < 1 or width < 1:
+                raise RuntimeError("Error")  # empty result: cpp_neighbors/wrapper.cpp:201-205
+            if width == tab.limit and not idx64:
+                return tab.rows
+            return ops.pack_rows(tab.rows, width, idx64)
+
+        n_levels = len(level_points)
+        up_tabs += [None] * (n_levels - len(up_tabs))
+        data = {
+            'points': level_points,
+            'neighbors': [finish(t) for t in conv_tabs],
+            'pools': [finish(t) for t in pool_tabs],
+            'upsamples': [finish(t) for t in up_tabs],
+            'stack_lengths': level_lens,
+        }
+        if in_device.type != "cuda":
+            data = {k: [t.to(in_device) for t in v] for k, v in data.items()}
+        return data
+
+
+class KPFEncoder(torch.nn.Module):
+    def __init__(self, config, d_bottle, increase_channel_when_downsample=True):
+        super().__init__()
+        self.logger = logging.getLogger(__name__)
+
+        octave = 0
+        r = config.first_subsampling_dl * config.conv_radius
+        in_dim = config.in_feats_dim
+        out_dim = config.first_feats_dim
+
+        self.encoder_blocks = nn.ModuleList()
+        self.encoder_skip_dims = []
+        self.encoder_skips = []
+
+        block = None
+        for block_i, block in enumerate(config.architecture):
+            if ('equivariant' in block) and (not out_dim % 3 == 0):
+                raise ValueError('Equivariant block but features dimension is not a factor of 3')
+            if any(tag in block for tag in ('pool', 'strided', 'upsample', 'global')):
+                self.encoder_skips.append(block_i)
+                self.encoder_skip_dims.append(in_dim)
+            if 'upsample' in block:
+                break
+            self.encoder_blocks.append(block_decider(block, r, in_dim, out_dim, octave, config, flag=True))
+            in_dim = out_dim // 2 if 'simple' in block else out_dim
+            if 'pool' in block or 'strided' in block:
+                octave += 1
+                r *= 2
+                if increase_channel_when_downsample:
+                    out_dim *= 2
+
+        if block is not None and 'upsample' not in block:
+            # no decoder: the last block is a skip position too
+            self.encoder_skips.append(block_i)
+            self.encoder_skip_dims.append(in_dim)
+
+    def forward(self, x, batch):
+        skip_x = []
+        for block_i, block_op in enumerate(self.encoder_blocks):
+            if block_i in self.encoder_skips:
+                skip_x.append(x)
+            x = block_op(x, batch)
+        return x, skip_x

@@ -1,0 +1,226 @@
+"""Device-tensor operators over the C ABI (``include/kpreg_b200.h``).
+
+Everything here takes and returns CUDA tensors and enqueues work on the current CUDA stream
+without synchronising the host.  Shapes that depend on the data (number of subsampled points,
+neighbour row widths) are returned as small device tensors; the callers in ``cpp_wrappers.py`` and
+``kpconv.py`` decide when to read them.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+AGGREGATION = {"sum": 0, "closest": 1}
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t, name)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t, name)
+    return t.detach().to(torch.int32).contiguous()
+
+
+def _idx(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    _lib.require_cuda(t, name)
+    if t.dtype == torch.int64:
+        return t.contiguous(), 1
+    if t.dtype == torch.int32:
+        return t.contiguous(), 0
+    return t.to(torch.int64).contiguous(), 1
+
+
+# ------------------------------------------------------------------------------------------------
+# subsampling
+# ------------------------------------------------------------------------------------------------
+
+def subsample(points: torch.Tensor, lens: torch.Tensor, sample_dl: float, max_p: int = 0):
+    """Voxel-grid barycentres of a stacked batch (kpreg_subsample_batch).
+
+    Returns (out_pts [N,3] — only the first M rows are valid, counts int32 [B+2] =
+    per-cloud counts, M, status).  Nothing is synchronised.
+    """
+    lib = _lib.load()
+    points = _f32c(points, "points")
+    lens = _i32c(lens, "lens")
+    n, b = points.shape[0], lens.shape[0]
+    dev = points.device
+    out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+    counts = torch.empty(b + 2, dtype=torch.int32, device=dev)
+    nbytes = _lib.size_query("kpreg_subsample_workspace_bytes", n, b)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_subsample_batch(points.data_ptr(), lens.data_ptr(), n, b, float(sample_dl), int(max_p),
+                                   out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_subsample_batch")
+    return out[:n], counts
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbours
+# ------------------------------------------------------------------------------------------------
+
+class CellGrid:
+    """Supports binned into cells of edge ``cell`` (kpreg_grid_build); serves radius queries with
+    radius <= cell for any query set of the same batch (kpreg_grid_query)."""
+
+    def __init__(self, supports: torch.Tensor, s_lens: torch.Tensor, cell: float):
+        lib = _lib.load()
+        self.supports = _f32c(supports, "supports")
+        self.s_lens = _i32c(s_lens, "s_batches")
+        self.n = int(self.supports.shape[0])
+        self.n_clouds = int(self.s_lens.shape[0])
+        self.cell = float(cell)
+        dev = self.supports.device
+        nbytes = _lib.size_query("kpreg_grid_workspace_bytes", self.n, self.n_clouds)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = lib.kpreg_grid_build(self.supports.data_ptr(), self.s_lens.data_ptr(), self.n, self.n_clouds,
+                                  self.cell, self.buf.data_ptr(), self.buf.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "kpreg_grid_build")
+
+    def query(self, queries: torch.Tensor, q_lens: torch.Tensor, radius: float, width: int,
+              stats: Optional[torch.Tensor] = None, want_counts: bool = False, idx64: bool = False):
+        """Rows of ascending-(d2, index) neighbours, truncated/padded to ``width`` columns.
+
+        Returns (idx [Nq,width], counts [Nq] or None, stats int32 [2] = {max count, status})."""
+        lib = _lib.load()
+        queries = _f32c(queries, "queries")
+        q_lens = _i32c(q_lens, "q_batches")
+        if q_lens.shape[0] != self.n_clouds:
+            raise RuntimeError("queries and supports must have the same number of clouds")
+        dev = queries.device
+        nq = int(queries.shape[0])
+        out = torch.empty((nq, width), dtype=torch.int64 if idx64 else torch.int32, device=dev)
+        counts = torch.empty(nq, dtype=torch.int32, device=dev) if want_counts else None
+        if stats is None:
+            stats = torch.zeros(2, dtype=torch.int32, device=dev)
+        rc = lib.kpreg_grid_query(self.buf.data_ptr(), self.n, self.n_clouds, queries.data_ptr(), q_lens.data_ptr(),
+                                  nq, float(radius), int(width), 1 if idx64 else 0, out.data_ptr(),
+                                  _lib.ptr(counts), stats.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, "kpreg_grid_query")
+        return out, counts, stats
+
+
+def pack_rows(rows: torch.Tensor, out_width: int, idx64: bool) -> torch.Tensor:
+    """[n, in_width] int32 -> [n, out_width] int32/int64 (kpreg_pack_rows)."""
+    lib = _lib.load()
+    _lib.require_cuda(rows, "rows")
+    rows = rows.contiguous()
+    n, in_w = rows.shape
+    out = torch.empty((n, out_width), dtype=torch.int64 if idx64 else torch.int32, device=rows.device)
+    rc = lib.kpreg_pack_rows(rows.data_ptr(), n, in_w, int(out_width), 1 if idx64 else 0, out.data_ptr(),
+                             _lib.stream_ptr(rows.device))
+    _lib.check(rc, "kpreg_pack_rows")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# KPConv
+# ------------------------------------------------------------------------------------------------
+
+def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: float, influence: str = "linear",
+                   aggregation: str = "sum", gemm: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    if influence not in INFLUENCE:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if aggregation not in AGGREGATION:
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    q_pts, s_pts, x = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
+    weights, kernel_points = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
+    idx, idx64 = _idx(idx, "neighb_inds")
+    n_q, n_s, h = q_pts.shape[0], s_pts.shape[0], idx.shape[1] if idx.dim() == 2 else 0
+    k, c_in, c_out = weights.shape
+    if x.shape[0] != n_s or x.shape[1] != c_in or idx.shape[0] != n_q or kernel_points.shape[0] != k:
+        raise RuntimeError("KPConv: inconsistent shapes")
+    dev = q_pts.device
+    out = torch.empty((n_q, c_out), dtype=torch.float32, device=dev)
+    nbytes = _lib.size_query("kpreg_kpconv_workspace_bytes", n_q, n_s, k, c_in, c_out, 0)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_kpconv_forward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
+                                  weights.data_ptr(), kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
+                                  float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation], int(gemm),
+                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_kpconv_forward")
+    return out
+
+
+def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_extent: float,
+                    influence: str = "linear", aggregation: str = "sum"):
+    """Returns (d_x [n_s,c_in], d_weights [K,c_in,c_out])."""
+    lib = _lib.load()
+    q_pts, s_pts, x = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
+    weights, kernel_points = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
+    grad_out = _f32c(grad_out, "grad_out")
+    idx, idx64 = _idx(idx, "neighb_inds")
+    n_q, n_s, h = q_pts.shape[0], s_pts.shape[0], idx.shape[1] if idx.dim() == 2 else 0
+    k, c_in, c_out = weights.shape
+    dev = q_pts.device
+    d_x = torch.empty((n_s, c_in), dtype=torch.float32, device=dev)
+    d_w = torch.empty((k, c_in, c_out), dtype=torch.float32, device=dev)
+    nbytes = _lib.size_query("kpreg_kpconv_workspace_bytes", n_q, n_s, k, c_in, c_out, 1)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_kpconv_backward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
+                                   weights.data_ptr(), kernel_points.data_ptr(), grad_out.data_ptr(), n_q, n_s, h, k,
+                                   c_in, c_out, float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                                   d_x.data_ptr(), d_w.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_kpconv_backward")
+    return d_x, d_w
+
+
+# ------------------------------------------------------------------------------------------------
+# max pool
+# ------------------------------------------------------------------------------------------------
+
+def max_pool_forward(x, idx, want_argmax: bool = False):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    idx, idx64 = _idx(idx, "inds")
+    n_s, c = x.shape
+    n_q, h = idx.shape
+    out = torch.empty((n_q, c), dtype=torch.float32, device=x.device)
+    arg = torch.empty((n_q, c), dtype=torch.int32, device=x.device) if want_argmax else None
+    rc = lib.kpreg_max_pool_forward(x.data_ptr(), idx.data_ptr(), idx64, n_q, n_s, h, c, out.data_ptr(),
+                                    _lib.ptr(arg), _lib.stream_ptr(x.device))
+    _lib.check(rc, "kpreg_max_pool_forward")
+    return out, arg
+
+
+def max_pool_backward(grad_out, argmax, n_s: int):
+    lib = _lib.load()
+    grad_out = _f32c(grad_out, "grad_out")
+    n_q, c = grad_out.shape
+    d_x = torch.empty((n_s, c), dtype=torch.float32, device=grad_out.device)
+    rc = lib.kpreg_max_pool_backward(grad_out.data_ptr(), argmax.data_ptr(), n_q, n_s, c, d_x.data_ptr(),
+                                     _lib.stream_ptr(grad_out.device))
+    _lib.check(rc, "kpreg_max_pool_backward")
+    return d_x
+
+
+# ------------------------------------------------------------------------------------------------
+# Kabsch
+# ------------------------------------------------------------------------------------------------
+
+def kabsch(a: torch.Tensor, b: torch.Tensor, w: Optional[torch.Tensor], n_sets: int, pts_per_set: int,
+           offsets: Optional[torch.Tensor] = None, threshold: float = -1.0, write_back: bool = False) -> torch.Tensor:
+    """a, b [total,3] f32 (contiguous), w [total] f32 or None -> [n_sets,3,4] (kpreg_kabsch).
+
+    ``w`` is modified in place when write_back is set (it must then be contiguous float32)."""
+    lib = _lib.load()
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    if w is not None:
+        _lib.require_cuda(w, "weights")
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            if write_back:
+                raise RuntimeError("in-place weight thresholding needs a contiguous float32 tensor")
+            w = w.to(torch.float32).contiguous()
+    out = torch.empty((n_sets, 3, 4), dtype=torch.float32, device=a.device)
+    rc = lib.kpreg_kabsch(a.data_ptr(), b.data_ptr(), _lib.ptr(w), _lib.ptr(offsets), int(n_sets), int(pts_per_set),
+                          float(threshold), 1 if write_back else 0, out.data_ptr(), _lib.stream_ptr(a.device))
+    _lib.check(rc, "kpreg_kabsch")
+    return out

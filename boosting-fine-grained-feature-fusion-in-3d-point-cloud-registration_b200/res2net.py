@@ -1,0 +1,71 @@
+"""The fork's "fine-grained feature fusion" unit: a Res2Net-style multi-scale MLP on point features.
+
+Mirror of ``my_Bottle2neck`` / ``my_res2Net`` in the reference's ``models/backbone_kpconv/res2net.py``
+(:84-159, :231-265) with identical sub-module names (``layer1.0.conv1``, ``bn1``, ``convs.i``, ``bns.i``,
+``conv3``, ``bn3``, ``downsample.0/1``) so checkpoints are interchangeable.  These are small dense
+Linear + BatchNorm1d + ReLU layers on [N, C] tensors; they stay on stock PyTorch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+
+class my_Bottle2neck(nn.Module):
+    """Linear(in -> w*s) -> split into s groups of width w; group i (i < s-1) is passed through its own
+    Linear+BN+ReLU after adding the previous group's output (hierarchical residual); the last group is
+    passed through unchanged; concat -> Linear(w*s -> planes) + BN, residual (optionally projected), ReLU."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, baseWidth=26, scale=4, stype='normal'):
+        super().__init__()
+        width = int(math.floor(planes * (baseWidth / 64.0)))
+        self.conv1 = nn.Linear(inplanes, width * scale, bias=False)
+        self.bn1 = nn.BatchNorm1d(width * scale)
+        self.nums = 1 if scale == 1 else scale - 1
+        if stype == 'stage':
+            self.pool = nn.AvgPool1d(kernel_size=3, stride=stride, padding=1)
+        self.convs = nn.ModuleList([nn.Linear(width, width, bias=False) for _ in range(self.nums)])
+        self.bns = nn.ModuleList([nn.BatchNorm1d(width) for _ in range(self.nums)])
+        self.conv3 = nn.Linear(width * scale, planes, bias=False)
+        self.bn3 = nn.BatchNorm1d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stype = stype
+        self.scale = scale
+        self.width = width
+
+    def forward(self, x):
+        groups = torch.split(self.relu(self.bn1(self.conv1(x))), self.width, 1)
+        outs, carry = [], None
+        for i in range(self.nums):
+            carry = groups[i] if (i == 0 or self.stype == 'stage') else carry + groups[i]
+            carry = self.relu(self.bns[i](self.convs[i](carry)))
+            outs.append(carry)
+        if self.scale != 1:
+            outs.append(groups[self.nums] if self.stype == 'normal' else self.pool(groups[self.nums]))
+        out = self.bn3(self.conv3(torch.cat(outs, 1)))
+        residual = x if self.downsample is None else self.downsample(x)
+        return self.relu(out + residual)
+
+
+class my_res2Net(nn.Module):
+    """One ``block`` mapping in_dim -> out_dim channels, with a Linear+BN projection on the residual."""
+
+    def __init__(self, block, in_dim, out_dim, baseWidth=26, scale=4):
+        super().__init__()
+        self.inplanes = in_dim
+        self.out_dim = out_dim
+        self.baseWidth = baseWidth
+        self.scale = scale
+        downsample = None
+        if self.inplanes != out_dim * block.expansion:
+            downsample = nn.Sequential(nn.Linear(self.inplanes, self.out_dim, bias=False),
+                                       nn.BatchNorm1d(self.out_dim))
+        self.layer1 = nn.Sequential(block(self.inplanes, out_dim, 1, downsample=downsample, stype='normal',
+                                          baseWidth=baseWidth, scale=scale))
+
+    def forward(self, x):
+        return self.layer1(x)

@@ -1,0 +1,146 @@
+/*
+ * kpreg_b200.h — C ABI of libkpreg_b200.so: the KPConv registration hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary.  Every entry point replaces one native/operator interface of the reference
+ * (YHY138/Boosting-Fine-grained-Feature-Fusion-in-3D-Point-Cloud-Registration); citations are
+ * relative to that repository.  Conventions:
+ *   - every data pointer is a DEVICE pointer owned by the caller (the Python host allocates with
+ *     torch); nothing is allocated, retained or freed by the library; scratch comes from a
+ *     caller-provided workspace whose size the matching *_workspace_bytes() call returns;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     the host.  Data-dependent sizes (subsampled point counts, neighbour row widths) are written
+ *     to device memory; the host reads them when it needs a shape;
+ *   - return value 0 = success; non-zero = KPREG_E_* (the Python host raises RuntimeError, the
+ *     error convention of the reference's CPython wrappers, cpp_neighbors/wrapper.cpp:75-205);
+ *   - point arrays are [N,3] float32 row-major ("stacked clouds", first all points of cloud 0,
+ *     then cloud 1, ...) with an int32 length per cloud, exactly the reference's batch layout
+ *     (cpp_subsampling/wrapper.cpp:62-333).
+ */
+#ifndef KPREG_B200_H
+#define KPREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KPREG_API __attribute__((visibility("default")))
+#else
+#define KPREG_API
+#endif
+
+#define KPREG_OK 0
+#define KPREG_E_INVALID 1   /* bad argument (null pointer, negative size, unsupported mode) */
+#define KPREG_E_WORKSPACE 2 /* workspace too small */
+#define KPREG_E_CUDA 3      /* a CUDA runtime call failed; see kpreg_last_error() */
+#define KPREG_E_RANGE 4     /* reported through the device status word: grid too large to index */
+
+/* Library / build identification. */
+KPREG_API int kpreg_version(void);                /* 100 * major + minor */
+KPREG_API const char* kpreg_last_error(void);     /* text of the last KPREG_E_CUDA on this thread */
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+KPREG_API unsigned long long kpreg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel-grid barycentre subsampling of a stacked batch.
+ * Replaces batch_grid_subsampling()            cpp_subsampling/grid_subsampling/grid_subsampling.cpp:109-211
+ * behind cpp_subsampling.subsample_batch()      cpp_subsampling/wrapper.cpp:62-333 (points-only branch,
+ * the only one the repository uses: models/backbone_kpconv/finegrained_kpconv.py:371).
+ *
+ * out_pts   [N,3] capacity; the first out_counts[n_clouds] rows are valid, cloud after cloud, each
+ *           cloud in the reference's std::unordered_map iteration order with fp32 barycentres that
+ *           are bit-identical to the reference's.
+ * out_counts[n_clouds+2]: per-cloud subsampled counts, then their total M, then a status word
+ *           (0 or KPREG_E_RANGE).
+ * max_p     < 1 = keep everything (grid_subsampling.cpp:134-135); else keep the first max_p per cloud.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_subsample_workspace_bytes(int64_t n_points, int n_clouds, size_t* bytes);
+KPREG_API int kpreg_subsample_batch(const float* pts, const int32_t* lens, int64_t n_points, int n_clouds,
+                          float sample_dl, int max_p, float* out_pts, int32_t* out_counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Radius neighbours of a stacked batch.
+ * Replaces batch_nanoflann_neighbors()          cpp_neighbors/neighbors/neighbors.cpp:211-332
+ * behind cpp_neighbors.batch_query()             cpp_neighbors/wrapper.cpp:58-238
+ * and batch_neighbors_kpconv()'s truncation      models/backbone_kpconv/finegrained_kpconv.py:248-263.
+ *
+ * A support set is binned once into a cell grid (kpreg_grid_build) and can then serve any number
+ * of query sets with radius <= the grid's cell size (conv, pool and upsample tables of one pyramid
+ * level share their supports).  kpreg_grid_query takes the same n_supports / n_clouds the grid was
+ * built with; the query batch must have the same number of clouds.
+ *
+ * kpreg_grid_query writes, for query i, the support indices (global = local + cloud offset) with
+ * fp32 d2 = (dx*dx + dy*dy) + dz*dz < radius*radius, ascending by (d2, index), truncated to
+ * `width` columns and padded with n_supports — the reference's row format.
+ *   out_idx     [n_queries, width] int32 (or int64 when idx64 != 0)
+ *   out_counts  optional [n_queries] int32: untruncated neighbour count per query
+ *   out_stats   [2] int32, accumulated with max: {max untruncated count, status}; zero it first.
+ * The reference's row width is min(out_stats[0], limit).
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_grid_workspace_bytes(int64_t n_supports, int n_clouds, size_t* bytes);
+KPREG_API int kpreg_grid_build(const float* supports, const int32_t* s_lens, int64_t n_supports, int n_clouds,
+                     float cell, void* grid, size_t grid_bytes, void* stream);
+KPREG_API int kpreg_grid_query(const void* grid, int64_t n_supports, int n_clouds, const float* queries,
+                     const int32_t* q_lens, int64_t n_queries, float radius, int width, int idx64,
+                     void* out_idx, int32_t* out_counts, int32_t* out_stats, void* stream);
+/* Re-pack [n_rows, in_width] int32 rows to [n_rows, out_width] (out_width <= in_width), int32 or int64. */
+KPREG_API int kpreg_pack_rows(const int32_t* in, int64_t n_rows, int in_width, int out_width, int idx64,
+                    void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * KPConv (rigid) forward / backward.
+ * Replaces KPConv.forward()   models/backbone_kpconv/finegrained_kpconv_blocks.py:265-401
+ * (deformable=False branch; influence 'constant'|'linear'|'gaussian'; aggregation 'sum'|'closest';
+ * including this fork's division by the number of neighbours with a positive feature sum, :396-399).
+ *
+ *   q_pts [n_q,3], s_pts [n_s,3] f32; idx [n_q,H] int32/int64 (pad value >= n_s = shadow);
+ *   x [n_s,c_in] f32; weights [K,c_in,c_out] f32; kernel_points [K,3] f32; out [n_q,c_out] f32.
+ *   influence: 0 constant, 1 linear, 2 gaussian.   aggregation: 0 sum, 1 closest.
+ *   gemm: 0 = fp32 CUDA-core contraction, 1 = tcgen05 (3xTF32 split, fp32-accurate) contraction.
+ * Backward returns d_x [n_s,c_in] and d_weights [K,c_in,c_out] (both overwritten).
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_kpconv_workspace_bytes(int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out,
+                                 int backward, size_t* bytes);
+KPREG_API int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, const void* idx, int idx64,
+                         const float* x, const float* weights, const float* kernel_points,
+                         int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out,
+                         float kp_extent, int influence, int aggregation, int gemm, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+KPREG_API int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, const void* idx, int idx64,
+                          const float* x, const float* weights, const float* kernel_points,
+                          const float* grad_out, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
+                          int c_in, int c_out, float kp_extent, int influence, int aggregation,
+                          float* d_x, float* d_weights, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Strided-block shortcut pooling.
+ * Replaces max_pool()         models/backbone_kpconv/finegrained_kpconv_blocks.py:125-141
+ * (max over the gathered rows of [x; 0]: a shadow index contributes the zero row).
+ *   argmax [n_q,c] int32 receives the winning support row (n_s for the shadow row); may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_max_pool_forward(const float* x, const void* idx, int idx64, int64_t n_q, int64_t n_s,
+                           int n_nbrs, int channels, float* out, int32_t* argmax, void* stream);
+KPREG_API int kpreg_max_pool_backward(const float* grad_out, const int32_t* argmax, int64_t n_q, int64_t n_s,
+                            int channels, float* d_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weighted Kabsch rigid-transform estimation for many correspondence sets.
+ * Replaces compute_rigid_transform()       utils/se3_torch.py:131-173
+ * and      fast_compute_rigid_transform()  utils/se3_torch.py:226-274 (weights <= threshold are
+ * zeroed first, and — like the reference, :240-242 — written back when write_back != 0).
+ *   a, b [total,3] f32; w [total] f32 or NULL (unweighted mean); set s covers rows
+ *   offsets[s] .. offsets[s+1] (offsets int64 [n_sets+1]); if offsets is NULL every set has
+ *   pts_per_set rows.  threshold < 0 disables thresholding.  out [n_sets,3,4] f32 = [R | t].
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_kabsch(const float* a, const float* b, float* w, const int64_t* offsets, int64_t n_sets,
+                 int64_t pts_per_set, float threshold, int write_back, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPREG_B200_H */

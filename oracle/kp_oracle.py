@@ -420,3 +420,16 @@ def se3_compare(a, b):
     tr = rot[..., 0, 0] + rot[..., 1, 1] + rot[..., 2, 2]
     deg = torch.acos(torch.clamp(0.5 * (tr - 1), -1.0, 1.0)) * 180.0 / math.pi
     return {"rot_deg": deg, "trans": trans.norm(dim=-1)}
+
+
+def pose_error(a, b):
+    """Well-conditioned pose difference for the parity tolerances (1e-3 deg, 1e-5 m): the rotation
+    angle of Ra Rb^T from the Frobenius norm, theta = 2 asin(|Ra Rb^T - I|_F / (2 sqrt 2)) (the
+    acos-of-trace form of se3_compare cannot resolve angles below ~0.03 deg in fp32), and |ta - tb|."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    rel = a[..., :3, :3] @ b[..., :3, :3].transpose(-1, -2)
+    eye = torch.eye(3, dtype=torch.float64).expand_as(rel)
+    fro = (rel - eye).flatten(-2).norm(dim=-1)
+    deg = 2.0 * torch.asin(torch.clamp(fro / (2.0 * math.sqrt(2.0)), max=1.0)) * 180.0 / math.pi
+    return {"rot_deg": deg, "trans": (a[..., :3, 3] - b[..., :3, 3]).norm(dim=-1)}
