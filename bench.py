@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — pairs/sec through the KPConv registration hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one batch of P synthetic 3DMatch-shape pairs per GPU (BASELINE configs[1]: ~20 k points per
+cloud after a 2.5 cm voxel grid, 4-level pyramid, neighborhood_limits 40, K = 15) through
+subsample pyramid + all neighbour / pool / upsample tables + KPFEncoder forward + weighted Kabsch.
+
+Printed JSON (rank 0):
+  value   whole-job pairs/s with the clouds already resident in HBM (device-timed, max over ranks)
+  e2e     the same metric through the public API from pinned HOST clouds (H2D of the step's clouds and
+          D2H of its poses + errors inside the timed region)
+  roofline      dominant kernel family: algorithmic bytes (or flops) / device time (CUDA events recorded
+                by the library around its launches, inside the timed region) vs MEASURED_PEAKS.json
+  cpu_baseline  (N=1, rank 0) the reference path on the host cores, bounded sample
+--impl reference times the reference's own CPU path (compiled reference C++ behind oracle/_ref when
+present + the torch-CPU restatement of its encoder / Kabsch) on the same workload, one pair per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "point-cloud pairs/sec (subsample+neighbours+KPConv+Kabsch)"
+UNIT = "pairs/s"
+WORKLOAD = "3DMatch-shape synthetic pairs (~20k pts/cloud, voxel 0.025 m, 4-level KPConv pyramid)"
+
+
+def make_pairs(n_pairs, seed0):
+    from kpreg_b200 import synthetic
+    pairs = [synthetic.threedmatch_pair(seed=seed0 + i) for i in range(n_pairs)]
+    return [p[0] for p in pairs], [p[1] for p in pairs], np.stack([p[2] for p in pairs])
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kpconv_work(meta, cfg):
+    """Algorithmic bytes / flops of the step's KPConv calls and neighbour queries (SURVEY.md §8d formulas)."""
+    n = [int(p.shape[0]) for p in meta["points"]]
+    k = cfg.num_kernel_points
+    out_dim, in_dim, layer = cfg.first_feats_dim, cfg.in_feats_dim, 0
+    gather_bytes = contract_flops = gather_flops = 0
+    for name in cfg.architecture:
+        strided = "strided" in name
+        if name.startswith("simple"):
+            c_in, c_out = in_dim, out_dim // 2
+        else:
+            c_in = c_out = out_dim // 4
+        n_s, n_q = n[layer], n[layer + 1] if strided else n[layer]
+        h = int(meta["pools"][layer].shape[1] if strided else meta["neighbors"][layer].shape[1])
+        # KPConv: idx + points + x + out + weights, each touched once
+        gather_bytes += 4 * n_q * h + 12 * (n_s + n_q) + 4 * n_s * c_in + 4 * n_q * c_out + 4 * k * c_in * c_out
+        gather_flops += 2 * n_q * k * h * c_in + 12 * n_q * h * k
+        contract_flops += 2 * n_q * k * c_in * c_out
+        in_dim = out_dim // 2 if name.startswith("simple") else out_dim
+        if strided:
+            layer += 1
+            out_dim *= 2
+    query_bytes = 0
+    for lvl in range(len(n)):
+        w = int(meta["neighbors"][lvl].shape[1])
+        query_bytes += 12 * 2 * n[lvl] + 4 * n[lvl] * w
+        if lvl + 1 < len(n):
+            query_bytes += 12 * (n[lvl] + n[lvl + 1]) + 4 * n[lvl + 1] * int(meta["pools"][lvl].shape[1])
+            query_bytes += 12 * (n[lvl] + n[lvl + 1]) + 4 * n[lvl] * int(meta["upsamples"][lvl].shape[1])
+    sub_bytes = sum(12 * n[l] + 12 * n[l + 1] for l in range(len(n) - 1))
+    return {"kpconv_bytes": gather_bytes, "gather_flops": gather_flops, "contract_flops": contract_flops,
+            "query_bytes": query_bytes, "subsample_bytes": sub_bytes}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference path (oracle): test/bench infrastructure, never the product
+# ------------------------------------------------------------------------------------------------------
+
+class CpuReference:
+    def __init__(self, cfg, state_dict):
+        import kp_oracle
+        self.o = kp_oracle
+        kp_oracle.build()
+        self.impl = "ref" if kp_oracle.have_ref() else "port"
+        self.cfg = cfg
+        self.sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+
+    def pair(self, src, tgt, pose, seed=0):
+        """One pair through preprocess -> encoder -> Kabsch on the host.  Returns stage seconds."""
+        from kpreg_b200.pipeline import synthetic_correspondences
+        t0 = time.perf_counter()
+        meta = self.o.preprocess([src, tgt], self.cfg, impl=self.impl)
+        t1 = time.perf_counter()
+        x0 = np.ones((meta["points"][0].shape[0], 1), np.float32)
+        with torch.no_grad():
+            self.o.encoder_forward(self.sd, self.cfg, x0, meta)
+        t2 = time.perf_counter()
+        lens = [int(v) for v in meta["stack_lengths"][-1]]
+        a, b, w = synthetic_correspondences(torch.from_numpy(meta["points"][-1]), lens, torch.from_numpy(pose)[None], seed=seed)
+        t3 = time.perf_counter()
+        self.o.fast_compute_rigid_transform(a[0], b[0], w[0], 0.85)
+        t4 = time.perf_counter()
+        return {"preprocess": t1 - t0, "encoder": t2 - t1, "kabsch": t4 - t3}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import kpreg_b200  # noqa: F401
+    from kpreg_b200 import kpconv_config
+    from kpreg_b200.kpconv import KPFEncoder
+    cfg = kpconv_config("3dmatch")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    enc = KPFEncoder(cfg, cfg.d_embed).eval()
+    ref = CpuReference(cfg, enc.state_dict())
+    src, tgt, poses = make_pairs(1, 1000)
+    for _ in range(min(max(args.warmup, 0), 1)):  # bounded: at most one warm-up pair
+        ref.pair(src[0], tgt[0], poses[0])
+    stages, t_total = [], 0.0
+    for _ in range(args.steps):
+        st = ref.pair(src[0], tgt[0], poses[0])
+        stages.append(st)
+        t_total += sum(st.values())
+    value = args.steps / t_total
+    split = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    kind = "reference" if ref.impl == "ref" else "port"
+    sample = (f"{args.steps} steps x 1 pair of the workload; preprocess = "
+              f"{'unmodified reference C++ (oracle/_ref, 1 thread)' if ref.impl == 'ref' else 'C port'}, "
+              f"encoder/Kabsch = torch-CPU restatement of the reference ops on {ref.cores} threads; "
+              f"stage s/pair {json.dumps({k: round(v, 4) for k, v in split.items()})}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gemm", type=int, default=None, help="KPConv contraction: 0 fp32 CUDA cores, 1 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import kpreg_b200  # noqa: F401
+    from kpreg_b200 import _lib, kpconv_blocks, kpconv_config
+    from kpreg_b200.pipeline import RegistrationPath, gather_results, result_rows
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gemm is not None:
+        kpconv_blocks.DEFAULT_GEMM = args.gemm
+
+    cfg = kpconv_config("3dmatch")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    path = RegistrationPath(cfg, index_dtype=torch.int32, weights_threshold=0.85).eval().to(dev)
+
+    # weak scaling: every rank gets its own P pairs (global pair g = rank + world * local index)
+    src_np, tgt_np, poses_np = make_pairs(args.pairs, 1000 + 100 * rank)
+    src_host = [torch.from_numpy(a).pin_memory() for a in src_np]
+    tgt_host = [torch.from_numpy(a).pin_memory() for a in tgt_np]
+    poses_host = torch.from_numpy(poses_np).pin_memory()
+    src_dev = [a.to(dev) for a in src_host]
+    tgt_dev = [a.to(dev) for a in tgt_host]
+    poses_dev = poses_host.to(dev)
+    h2d_bytes = sum(a.numel() * 4 for a in src_host + tgt_host) + poses_host.numel() * 4
+    n_global = args.pairs * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        out = path(src_dev, tgt_dev, poses_dev)
+        rows = result_rows(out)
+        return gather_results(rows, n_global, rank, world), out
+
+    def step_e2e():
+        s = [a.to(dev, non_blocking=True) for a in src_host]
+        t = [a.to(dev, non_blocking=True) for a in tgt_host]
+        p = poses_host.to(dev, non_blocking=True)
+        out = path(s, t, p)
+        table = gather_results(result_rows(out), n_global, rank, world)
+        return table.cpu(), out  # D2H of every pair's pose + errors
+
+    def timed(fn, steps, warmup, profile):
+        for _ in range(warmup):
+            fn()
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = _lib.launch_count()
+        if profile:
+            _lib.profile(True)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        last = None
+        for i in range(steps):
+            starts[i].record()
+            last = fn()
+            ends[i].record()
+            flush.fill_(i & 1)  # evict L2 between timed steps (outside the events)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        fam = _lib.profile_read() if profile else None
+        if profile:
+            _lib.profile(False)
+        ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launch_count() - launches0, fam, last
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _, last_e2e = timed(step_e2e, args.steps, args.warmup, profile=False)
+
+    value = n_global * args.steps / (ms_total / 1000.0)
+    e2e_value = n_global * args.steps / (ms_e2e / 1000.0)
+    table, out = last
+    d2h_bytes = int(last_e2e[0].numel() * 4)
+
+    if rank == 0:
+        pk = peaks()
+        work = kpconv_work(out["meta"], cfg)
+        fam_ms = {k: v[0] / args.steps for k, v in fam.items()}
+        fam_n = {k: v[1] / args.steps for k, v in fam.items()}
+        top = max(("kpconv_gather", "kpconv_contract", "grid_query", "subsample"), key=lambda k: fam_ms[k])
+        if top == "kpconv_contract":
+            ach = work["contract_flops"] / (fam_ms[top] * 1e-3) / 1e12
+            roof = {"kernel": "kpconv contraction GEMM [Nq,K*Cin]x[K*Cin,Cout]", "bound": "tensor", "achieved": ach,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None}
+        else:
+            nbytes = {"kpconv_gather": work["kpconv_bytes"], "grid_query": work["query_bytes"],
+                      "subsample": work["subsample_bytes"]}[top]
+            ach = nbytes / (fam_ms[top] * 1e-3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None}
+        roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
+        roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
+        roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
+        roof["share_of_step"] = round(fam_ms[top] / (ms_total / args.steps), 4)
+        roof["algorithmic_per_step"] = work
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(cfg, path.kpf_encoder.state_dict())
+            ref.pair(src_np[0], tgt_np[0], poses_np[0])  # warm-up
+            n_s, t_s, stages = 2, 0.0, []
+            for i in range(n_s):
+                st = ref.pair(src_np[i % args.pairs], tgt_np[i % args.pairs], poses_np[i % args.pairs])
+                stages.append(st)
+                t_s += sum(st.values())
+            split = {k: round(float(np.mean([s[k] for s in stages])), 4) for k in stages[0]}
+            cpu = {"value": n_s / t_s, "unit": UNIT, "cores": ref.cores, "kind": "reference" if ref.impl == "ref" else "port",
+                   "sample": f"{n_s} pairs of the same workload after 1 warm-up pair; preprocess on the "
+                             f"{'unmodified reference C++ (oracle/_ref)' if ref.impl == 'ref' else 'C port'} (1 thread), encoder + "
+                             f"Kabsch = torch-CPU restatement on {ref.cores} threads; stage s/pair {json.dumps(split)}"}
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "global_pairs_per_step": n_global,
+                       "points_per_level": [int(p.shape[0]) for p in out["meta"]["points"]],
+                       "neighbor_widths": [int(t.shape[1]) for t in out["meta"]["neighbors"]],
+                       "kpconv_contraction": "tcgen05-3xTF32" if kpconv_blocks.DEFAULT_GEMM == 1 else "fp32-cuda-core",
+                       "parallelism": f"pairs sharded over {world} GPU(s); all-gather of [P,14] poses+errors",
+                       "l2": "256 MiB write between timed steps (outside the CUDA events)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "final_layer_pose_error": {"rot_deg_max": float(table[:, 12].max()), "trans_max": float(table[:, 13].max())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

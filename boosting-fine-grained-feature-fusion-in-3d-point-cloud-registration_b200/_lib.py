@@ -24,6 +24,8 @@ _SIGNATURES = {
     "kpreg_version": (_c_int, []),
     "kpreg_last_error": (ctypes.c_char_p, []),
     "kpreg_launch_count": (ctypes.c_ulonglong, []),
+    "kpreg_profile": (_c_int, [_c_int]),
+    "kpreg_profile_read": (_c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]),
     "kpreg_subsample_workspace_bytes": (_c_int, [_c_i64, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_subsample_batch": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_int, _c_ptr, _c_ptr,
                                        _c_ptr, _c_size, _c_ptr]),
@@ -93,6 +95,22 @@ def stream_ptr(device: torch.device) -> int:
 
 def launch_count() -> int:
     return int(load().kpreg_launch_count())
+
+
+FAMILIES = ("subsample", "grid_build", "grid_query", "kpconv_gather", "kpconv_contract", "max_pool", "kabsch", "other")
+
+
+def profile(enable: bool) -> None:
+    """Start (and clear) / stop per-kernel-family device timing."""
+    check(load().kpreg_profile(1 if enable else 0), "kpreg_profile")
+
+
+def profile_read() -> Dict[str, Tuple[float, int]]:
+    """{family: (summed device ms, timed launches)} since the last profile(True)."""
+    ms = (ctypes.c_double * len(FAMILIES))()
+    cnt = (ctypes.c_ulonglong * len(FAMILIES))()
+    check(load().kpreg_profile_read(ms, cnt), "kpreg_profile_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(FAMILIES)}
 
 
 class _Workspaces:

@@ -33,6 +33,14 @@ void count_launches(unsigned long long n);
     }                                                       \
   } while (0)
 
+// Times everything enqueued on `stream` during its lifetime when profiling is on (capi.cu).
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(int family, cudaStream_t s);
+  ~ProfScope();
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline int bits_for(uint64_t n) {  // bits needed to represent values < n

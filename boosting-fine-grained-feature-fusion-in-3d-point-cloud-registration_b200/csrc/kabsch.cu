@@ -171,6 +171,7 @@ extern "C" int kpreg_kabsch(const float* a, const float* b, float* w, const int6
   if (n_sets == 0) return KPREG_OK;
   if (!a || !b || !out) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
+  ProfScope prof(KPREG_FAM_KABSCH, stream);
   k_kabsch<<<(unsigned)n_sets, kKabschThreads, 0, stream>>>(a, b, w, offsets, pts_per_set, threshold, write_back, out);
   KP_LAUNCH_CHECK();
   return KPREG_OK;

@@ -323,6 +323,7 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   const int cap = kNumSMs * 32;
   if (blocks > cap) blocks = cap;
   const IdxT* ip = static_cast<const IdxT*>(idx);
+  ProfScope prof(KPREG_FAM_GATHER, stream);
 #define KP_GATHER(CPL)                                                                                                     \
   k_kpconv_gather<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, \
                                                                        n_kpts, c_in, extent, influence, aggregation, agg,  \
@@ -400,6 +401,7 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
                                       influence, aggregation, w.agg, w.inv_num, stream);
   if (rc) return rc;
   const int kd = n_kpts * c_in;
+  ProfScope prof(KPREG_FAM_CONTRACT, stream);
   if (gemm == 1) {
     rc = kpconv_gemm_tc_prepare_weights(weights, kd, c_out, w.w_split, stream);
     if (rc) return rc;

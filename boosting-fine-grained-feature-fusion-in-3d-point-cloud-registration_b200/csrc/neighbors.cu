@@ -359,6 +359,7 @@ extern "C" int kpreg_grid_build(const float* supports, const int32_t* s_lens, in
   cudaStream_t stream = (cudaStream_t)stream_;
   GridWs w = carve_grid(grid, n, n_clouds);
   if (w.total > grid_bytes) return KPREG_E_WORKSPACE;
+  ProfScope prof(KPREG_FAM_GRID_BUILD, stream);
   int rc = launch_cloud_offsets(s_lens, n_clouds, w.off, stream);
   if (rc) return rc;
   k_grid_init<<<1, 32, 0, stream>>>(w.bbox, w.hdr);
@@ -403,6 +404,7 @@ extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const
   int blocks = ceil_div(n_queries, kWarpsPerBlock);
   const int max_blocks = kNumSMs * 16;
   if (blocks > max_blocks) blocks = max_blocks;
+  ProfScope prof(KPREG_FAM_GRID_QUERY, stream);
   if (idx64) {
     k_grid_query<int64_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
                                                                      w.tab_cap, queries, q_off, n_queries, radius, r2, width,
@@ -425,6 +427,7 @@ extern "C" int kpreg_pack_rows(const int32_t* in, int64_t n_rows, int in_width, 
   const int64_t total = n_rows * (int64_t)out_width;
   int blocks = ceil_div(total, 256);
   if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  ProfScope prof(KPREG_FAM_OTHER, stream);
   if (idx64) k_pack_rows<int64_t><<<blocks, 256, 0, stream>>>(in, n_rows, in_width, out_width, static_cast<int64_t*>(out));
   else k_pack_rows<int32_t><<<blocks, 256, 0, stream>>>(in, n_rows, in_width, out_width, static_cast<int32_t*>(out));
   KP_LAUNCH_CHECK();

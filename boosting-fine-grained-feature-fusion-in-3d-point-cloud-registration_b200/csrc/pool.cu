@@ -60,6 +60,7 @@ extern "C" int kpreg_max_pool_forward(const float* x, const void* idx, int idx64
   if (!out || (n_nbrs > 0 && !idx) || (n_s > 0 && !x)) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int blocks = ceil_div(n_q * 32, 256);
+  ProfScope prof(KPREG_FAM_POOL, stream);
   if (idx64) k_max_pool<int64_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax);
   else k_max_pool<int32_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax);
   KP_LAUNCH_CHECK();

@@ -30,8 +30,9 @@ namespace {
 constexpr int kVoxelBits = 40;
 constexpr uint64_t kVoxelMask = (1ull << kVoxelBits) - 1ull;
 
-// Bucket counts of std::unordered_map<size_t,T> as it grows (oracle/gen_prime_growth.cpp re-derives
-// them from libstdc++ itself; tests/test_oracle.py checks this table against that header).
+// Bucket counts of std::unordered_map<size_t,T> as it grows from empty at load factor 1 (libstdc++
+// _Prime_rehash_policy: 13, then the next listed prime >= 2x).  The test suite re-derives the
+// sequence from libstdc++ itself and checks this table against it.
 __constant__ unsigned int c_table_sizes[27] = {
     13u,       29u,       59u,       127u,      257u,       541u,       1109u,
     2357u,     5087u,     10273u,    20753u,    42043u,     85229u,     172933u,
@@ -381,6 +382,7 @@ extern "C" int kpreg_subsample_batch(const float* pts, const int32_t* lens, int6
   SubsampleWs w = carve_subsample(workspace, n, n_clouds);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
 
+  ProfScope prof(KPREG_FAM_SUBSAMPLE, stream);
   KP_CUDA_TRY(cudaMemsetAsync(w.status, 0, 4 * sizeof(int32_t), stream));
   int rc = launch_cloud_offsets(lens, n_clouds, w.off, stream);
   if (rc) return rc;

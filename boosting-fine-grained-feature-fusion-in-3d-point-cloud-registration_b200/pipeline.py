@@ -1,0 +1,110 @@
+"""The registration hot path end to end, batched and pair-sharded.
+
+One step = for a batch of point-cloud pairs: KPConv pyramid (``Preprocessor``) -> ``KPFEncoder``
+forward -> weighted Kabsch pose per pair.  This is the slice of ``RegTR.forward`` that BASELINE.json
+names (reference models/finegrained_regtr.py:121, :139, :215-218).  The transformer / correspondence
+decoder that sits between the encoder and the pose solve in the reference is out of scope, so the
+correspondences fed to the Kabsch stage are synthetic but shaped like the decoder's output
+(``[6, N_src_c + N_tgt_c, 3]`` per pair on the coarsest pyramid level).
+
+Multi-GPU: pairs are independent, so they are sharded round-robin over ranks (one process per GPU) with
+no data-path collective; the only exchange is an all-gather of the per-pair ``[3,4]`` poses and the
+``(rot_deg, trans)`` errors (NCCL over NVLink; gloo on CPU for the tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .kpconv import KPFEncoder, Preprocessor
+from .se3_torch import compute_rigid_transform_batch, se3_compare
+
+N_DECODER_LAYERS = 6  # RegTR predicts a pose after each of its 6 decoder layers
+
+
+def shard_pairs(n_pairs: int, rank: int, world_size: int) -> List[int]:
+    """Pair i is processed by rank i mod world_size."""
+    return list(range(rank, n_pairs, world_size))
+
+
+def gather_results(local: torch.Tensor, n_pairs: int, rank: int, world_size: int) -> torch.Tensor:
+    """All-gather per-pair result rows.  ``local`` is [n_local, D] for the pairs of shard_pairs(); every
+    rank returns the full [n_pairs, D] table in pair order.  Shards are padded to equal length."""
+    if world_size == 1:
+        return local
+    per = (n_pairs + world_size - 1) // world_size
+    padded = torch.zeros((per, local.shape[1]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world_size * per, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    # row (r, j) of the gathered table is pair r + j*world_size
+    table = out.view(world_size, per, -1).transpose(0, 1).reshape(world_size * per, -1)
+    return table[:n_pairs]
+
+
+def synthetic_correspondences(coarse_pts: torch.Tensor, coarse_lens: Sequence[int], poses: torch.Tensor,
+                              noise: float = 0.01, seed: int = 0):
+    """Decoder-shaped correspondences for every pair of a stacked batch (first B clouds = sources, last B =
+    targets, the reference's ``split_src_tgt`` convention, utils/seq_manipulation.py:42-48).
+
+    For pair p: a = [src_c ; R^-1 (tgt_c - t) + n], b = [R src_c + t + n ; tgt_c], repeated for the 6
+    decoder layers with fresh noise, weights = sigmoid(N(0, 2)).  Returns lists (a, b, w) of
+    [6, Nc_p, 3] / [6, Nc_p] tensors on the device of ``coarse_pts``."""
+    n_pairs = len(coarse_lens) // 2
+    starts = [0]
+    for n in coarse_lens:
+        starts.append(starts[-1] + int(n))
+    gen = torch.Generator(device=coarse_pts.device)
+    gen.manual_seed(seed)
+    a_all, b_all, w_all = [], [], []
+    for p in range(n_pairs):
+        src = coarse_pts[starts[p]:starts[p + 1]]
+        tgt = coarse_pts[starts[n_pairs + p]:starts[n_pairs + p + 1]]
+        rot, trans = poses[p, :, :3], poses[p, :, 3]
+        n_c = src.shape[0] + tgt.shape[0]
+        a = torch.cat([src, (tgt - trans) @ rot], 0).expand(N_DECODER_LAYERS, n_c, 3)
+        b = torch.cat([src @ rot.T + trans, tgt], 0).expand(N_DECODER_LAYERS, n_c, 3)
+        jitter = noise * torch.randn((2, N_DECODER_LAYERS, n_c, 3), generator=gen, device=coarse_pts.device)
+        mask = torch.zeros((n_c, 1), device=coarse_pts.device)
+        mask[src.shape[0]:] = 1.0
+        a_all.append((a + jitter[0] * mask).contiguous())
+        b_all.append((b + jitter[1] * (1.0 - mask)).contiguous())
+        w_all.append(torch.sigmoid(2.0 * torch.randn((N_DECODER_LAYERS, n_c), generator=gen, device=coarse_pts.device)))
+    return a_all, b_all, w_all
+
+
+class RegistrationPath(torch.nn.Module):
+    """Preprocessor + KPFEncoder + batched Kabsch behind one call."""
+
+    def __init__(self, cfg, index_dtype: torch.dtype = torch.int32, weights_threshold: Optional[float] = None):
+        super().__init__()
+        self.cfg = cfg
+        self.preprocessor = Preprocessor(cfg, index_dtype=index_dtype)
+        self.kpf_encoder = KPFEncoder(cfg, cfg.d_embed)
+        self.weights_threshold = weights_threshold
+
+    @torch.no_grad()
+    def forward(self, src_xyz: Sequence[torch.Tensor], tgt_xyz: Sequence[torch.Tensor], poses_gt: torch.Tensor,
+                corr_seed: int = 0) -> Dict[str, torch.Tensor]:
+        """src_xyz / tgt_xyz: lists of [N_i,3] clouds (the batch dict of collate_pair,
+        data_loaders/collate_functions.py:13-22); poses_gt [B,3,4] seeds the synthetic correspondences.
+        Returns the encoder features, the per-layer poses [6,B,3,4] and the final-layer pose errors."""
+        n_pairs = len(src_xyz)
+        meta = self.preprocessor(list(src_xyz) + list(tgt_xyz))
+        feats0 = torch.ones((meta['points'][0].shape[0], 1), dtype=torch.float32, device=meta['points'][0].device)
+        feats, _ = self.kpf_encoder(feats0, meta)
+        coarse = meta['points'][-1]
+        lens = meta['stack_lengths'][-1].cpu().tolist()
+        a, b, w = synthetic_correspondences(coarse, lens, poses_gt.to(coarse.device), seed=corr_seed)
+        poses = compute_rigid_transform_batch(a, b, w, self.weights_threshold)
+        err = se3_compare(poses[-1], poses_gt.to(coarse.device))
+        return {'feats': feats, 'poses': poses, 'rot_deg': err['rot_deg'], 'trans': err['trans'], 'meta': meta,
+                'n_pairs': n_pairs}
+
+
+def result_rows(out: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """[B, 14] rows: the final-layer [3,4] pose flattened + (rot_deg, trans) — what the ranks exchange."""
+    pose = out['poses'][-1].reshape(-1, 12)
+    return torch.cat([pose, out['rot_deg'][:, None], out['trans'][:, None]], 1).contiguous()

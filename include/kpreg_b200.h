@@ -44,6 +44,22 @@ KPREG_API const char* kpreg_last_error(void);     /* text of the last KPREG_E_CU
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 KPREG_API unsigned long long kpreg_launch_count(void);
 
+/* Optional per-kernel-family device timing (CUDA events on the launching stream), used by bench.py for the
+ * roofline figures.  kpreg_profile(1) clears the records and starts recording, kpreg_profile(0) stops;
+ * kpreg_profile_read() waits for the recorded events and returns, per family, the summed device time in
+ * milliseconds and the number of timed launches.  Off by default (no events are recorded). */
+#define KPREG_FAM_SUBSAMPLE 0   /* whole subsample_batch call */
+#define KPREG_FAM_GRID_BUILD 1  /* whole grid_build call */
+#define KPREG_FAM_GRID_QUERY 2  /* k_grid_query */
+#define KPREG_FAM_GATHER 3      /* k_kpconv_gather */
+#define KPREG_FAM_CONTRACT 4    /* KPConv contraction GEMM */
+#define KPREG_FAM_POOL 5        /* k_max_pool */
+#define KPREG_FAM_KABSCH 6      /* k_kabsch */
+#define KPREG_FAM_OTHER 7       /* pack rows, row sums, backward kernels */
+#define KPREG_N_FAMILIES 8
+KPREG_API int kpreg_profile(int enable);
+KPREG_API int kpreg_profile_read(double* ms /*[KPREG_N_FAMILIES]*/, unsigned long long* launches /*[KPREG_N_FAMILIES]*/);
+
 /* ---------------------------------------------------------------------------------------------
  * Voxel-grid barycentre subsampling of a stacked batch.
  * Replaces batch_grid_subsampling()            cpp_subsampling/grid_subsampling/grid_subsampling.cpp:109-211

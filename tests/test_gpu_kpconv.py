@@ -1,0 +1,141 @@
+"""-m gpu: KPConv forward/backward, max-pool and the whole encoder on CUDA vs the reference's Python
+(golden vectors) and vs the CPU oracle.  Tolerance (north star): features within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+import kpreg_b200  # noqa: F401
+from kpreg_b200 import kpconv_config, ops, synthetic
+from kpreg_b200 import kpconv_blocks
+from kpreg_b200.kpconv import KPFEncoder, Preprocessor
+from kpreg_b200.kpconv_blocks import KPConv, max_pool
+from conftest import rel_err
+from gpu_util import LEVEL_KEYS, _levels, cuda
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # max|got - want| / max|want|
+
+
+@pytest.mark.parametrize("infl", ["linear", "gaussian", "constant"])
+@pytest.mark.parametrize("agg", ["sum", "closest"])
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_kpconv_forward_matches_reference(golden_modelnet, infl, agg, idx_dtype):
+    g = golden_modelnet
+    out = ops.kpconv_forward(cuda(g["mn_points_1"]), cuda(g["mn_points_0"]), cuda(g["mn_pools_0"], idx_dtype),
+                             cuda(g["op_x"]), cuda(g[f"op_{infl}_{agg}_w"]), cuda(g[f"op_{infl}_{agg}_kp"]), 0.12,
+                             infl, agg, gemm=0)
+    assert rel_err(out.cpu().numpy(), g[f"op_{infl}_{agg}_out"]) < TOL
+
+
+def test_kpconv_module_and_backward_match_reference(golden_modelnet):
+    g = golden_modelnet
+    np.random.seed(0)
+    conv = KPConv(15, 3, 24, 40, 0.12, 0.165).cuda()
+    conv.load_state_dict({"weights": torch.from_numpy(g["bw_w"]), "kernel_points": torch.from_numpy(g["bw_kp"])})
+    x = cuda(g["op_x"]).requires_grad_(True)
+    out = conv(cuda(g["mn_points_1"]), cuda(g["mn_points_0"]), cuda(g["mn_pools_0"]), x)
+    out.backward(cuda(g["bw_g"]))
+    assert rel_err(x.grad.cpu().numpy(), g["bw_dx"]) < TOL
+    assert rel_err(conv.weights.grad.cpu().numpy(), g["bw_dw"]) < TOL
+    assert conv.kernel_points.grad is None
+
+
+def test_max_pool_forward_backward(golden_modelnet):
+    g = golden_modelnet
+    x = cuda(g["op_x"]).requires_grad_(True)
+    out = max_pool(x, cuda(g["mn_pools_0"]))
+    assert np.array_equal(out.detach().cpu().numpy(), g["op_maxpool"])  # a max: exact
+    out.backward(cuda(g["bw_g"][:, :24]))
+    assert rel_err(x.grad.cpu().numpy(), g["bw_maxpool_dx"]) < 1e-6
+
+
+@pytest.mark.parametrize("c_in,c_out", [(1, 64), (32, 32), (64, 64), (128, 128), (256, 256), (40, 24)])
+def test_kpconv_forward_matches_oracle_channel_sweep(oracle, golden_modelnet, c_in, c_out):
+    """Every channel width the 3DMatch encoder uses (SURVEY.md §8a call table), + an odd one."""
+    g = golden_modelnet
+    rng = np.random.default_rng(c_in)
+    q, s, idx = g["mn_points_0"], g["mn_points_0"], g["mn_neighbors_0"]
+    x = np.ones((s.shape[0], 1), np.float32) if c_in == 1 else rng.normal(size=(s.shape[0], c_in)).astype(np.float32)
+    w = (rng.normal(size=(15, c_in, c_out)) / np.sqrt(15 * c_in)).astype(np.float32)
+    kp = g["op_linear_sum_kp"] * 0.5
+    want = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.06)
+    got = ops.kpconv_forward(cuda(q), cuda(s), cuda(idx), cuda(x), cuda(w), cuda(kp), 0.06, gemm=0)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < TOL
+
+
+def test_normalisation_counts_positive_feature_sums(oracle, golden_modelnet):
+    """The fork divides by the number of neighbours whose feature SUM is positive (blocks :396-399)."""
+    g = golden_modelnet
+    rng = np.random.default_rng(5)
+    q, s, idx = g["mn_points_0"], g["mn_points_0"], g["mn_neighbors_0"]
+    x = rng.normal(size=(s.shape[0], 8)).astype(np.float32)
+    x[::3] = -np.abs(x[::3])  # a third of the rows have a negative sum -> not counted
+    w = rng.normal(size=(15, 8, 16)).astype(np.float32)
+    kp = g["op_linear_sum_kp"] * 0.5
+    want = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.06)
+    got = ops.kpconv_forward(cuda(q), cuda(s), cuda(idx), cuda(x), cuda(w), cuda(kp), 0.06)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < TOL
+
+
+def _golden_encoder(g, cfg):
+    np.random.seed(0)
+    enc = KPFEncoder(cfg, 256)
+    sd = {k[len("mn_sd::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("mn_sd::")}
+    enc.load_state_dict(sd, strict=True)  # reference parameter names load unchanged
+    return enc.cuda()
+
+
+def test_encoder_matches_reference_eval(golden_modelnet):
+    g = golden_modelnet
+    cfg = kpconv_config("modelnet", first_feats_dim=64)
+    enc = _golden_encoder(g, cfg).eval()
+    batch = {key: [cuda(a) for a in _levels(g, "mn_", key)] for key in LEVEL_KEYS}
+    x0 = torch.ones((g["mn_points_0"].shape[0], 1), device="cuda")
+    with torch.no_grad():
+        y, skips = enc(x0, batch)
+    assert rel_err(y.cpu().numpy(), g["mn_enc_out"]) < TOL
+    assert len(skips) == 2 and rel_err(skips[1].cpu().numpy(), g["mn_enc_skip_1"]) < TOL
+
+
+def test_encoder_end_to_end_from_raw_clouds(golden_modelnet):
+    """Preprocessor (CUDA) -> KPFEncoder (CUDA) from the raw pair reproduces the reference's features."""
+    g = golden_modelnet
+    cfg = kpconv_config("modelnet", first_feats_dim=64)
+    enc = _golden_encoder(g, cfg).eval()
+    meta = Preprocessor(cfg)([cuda(g["mn_src"]), cuda(g["mn_tgt"])])
+    x0 = torch.ones((meta["points"][0].shape[0], 1), device="cuda")
+    with torch.no_grad():
+        y, _ = enc(x0, meta)
+    assert rel_err(y.cpu().numpy(), g["mn_enc_out"]) < TOL
+
+
+def test_encoder_training_step_gradients(golden_modelnet):
+    """forward + backward through every KPConv / max_pool of the encoder (BASELINE config 4 in small):
+    loss = sum(encoder output), BatchNorm in training mode, gradients vs the reference's autograd."""
+    g = golden_modelnet
+    cfg = kpconv_config("modelnet", first_feats_dim=64)
+    enc = _golden_encoder(g, cfg).train()
+    batch = {key: [cuda(a) for a in _levels(g, "mn_", key)] for key in LEVEL_KEYS}
+    x0 = torch.ones((g["mn_points_0"].shape[0], 1), device="cuda")
+    y, _ = enc(x0, batch)
+    y.sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), g["mn_enc_out_train"]) < 5 * TOL
+    assert rel_err(enc.encoder_blocks[1].KPConv.weights.grad.cpu().numpy(), g["mn_grad_kp1"]) < 1e-3
+    assert rel_err(enc.encoder_blocks[0].KPConv.weights.grad.cpu().numpy(), g["mn_grad_kp0"]) < 1e-3
+
+
+def test_encoder_3dmatch_full_size_vs_oracle(oracle):
+    """BASELINE config 2 shape (one pair, ~20k points per cloud), random-init weights."""
+    cfg = kpconv_config("3dmatch")
+    torch.manual_seed(1)
+    np.random.seed(1)
+    enc = KPFEncoder(cfg, cfg.d_embed).eval()
+    src, tgt, _ = synthetic.threedmatch_pair(seed=31, n_raw=20000)
+    meta = Preprocessor(cfg)([cuda(src), cuda(tgt)])
+    x0 = torch.ones((meta["points"][0].shape[0], 1))
+    want, _ = oracle.encoder_forward(enc.state_dict(), cfg, x0, {k: [t.cpu() for t in v] for k, v in meta.items()})
+    enc = enc.cuda()
+    with torch.no_grad():
+        got, _ = enc(x0.cuda(), meta)
+    assert got.shape[1] == 1024
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 5 * TOL  # 11 blocks deep

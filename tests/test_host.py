@@ -1,0 +1,93 @@
+"""CPU-side checks of the host mirror of the reference API (no kernels run)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kpreg_b200  # noqa: F401
+from kpreg_b200 import kpconv_config, synthetic
+from kpreg_b200.kernel_points import load_kernels
+from kpreg_b200.kpconv import KPFEncoder
+from kpreg_b200.kpconv_blocks import KPConv, ResnetBottleneckBlock, SimpleBlock, _segment_instance_norm, block_decider
+from kpreg_b200.pipeline import shard_pairs
+from conftest import GOLDEN, rel_err
+
+
+@pytest.mark.parametrize("name", ["3dmatch", "modelnet"])
+def test_encoder_state_dict_matches_reference_names_and_shapes(name):
+    """Reference checkpoints must load: same parameter / buffer names and shapes."""
+    want = json.load(open(os.path.join(GOLDEN, "encoder_state_dict_shapes.json")))[name]
+    np.random.seed(0)
+    cfg = kpconv_config(name)
+    enc = KPFEncoder(cfg, cfg.d_embed)
+    got = {k: list(v.shape) for k, v in enc.state_dict().items()}
+    assert got == want
+    if name == "3dmatch":
+        assert enc.encoder_skips == [2, 5, 8, 10] and enc.encoder_skip_dims == [128, 256, 512, 1024]
+        kinds = [type(b) for b in enc.encoder_blocks]
+        assert kinds[0] is SimpleBlock and all(k is ResnetBottleneckBlock for k in kinds[1:])
+        extents = [round(b.KPConv.KP_extent, 6) for b in enc.encoder_blocks]
+        assert extents == [0.05, 0.05, 0.05, 0.1, 0.1, 0.1, 0.2, 0.2, 0.2, 0.4, 0.4]
+
+
+def test_kpconv_constructor_and_errors():
+    np.random.seed(0)
+    conv = KPConv(15, 3, 8, 16, 0.05, 0.0625)
+    assert conv.weights.shape == (15, 8, 16) and conv.kernel_points.shape == (15, 3)
+    assert conv.weights.requires_grad and not conv.kernel_points.requires_grad
+    assert float(conv.kernel_points[0].norm()) < 0.0625 * 0.05  # 'center': point 0 stays at the origin (+noise)
+    assert float(conv.kernel_points.norm(dim=1).max()) < 0.0625
+    with pytest.raises(ValueError):
+        KPConv(15, 3, 8, 16, 0.05, 0.0625, KP_influence="cubic")
+    with pytest.raises(ValueError):
+        KPConv(15, 3, 8, 16, 0.05, 0.0625, aggregation_mode="mean")
+    with pytest.raises(ValueError):
+        block_decider("conv9", 0.1, 8, 16, 0, kpconv_config("3dmatch"))
+
+
+def test_load_kernels_reads_the_reference_ply_layout(tmp_path, monkeypatch):
+    """kernels/dispositions/k_015_center_3D.ply relative to the CWD wins over the generated disposition."""
+    pts = np.random.default_rng(0).normal(size=(15, 3))
+    pts[0] = 0
+    d = tmp_path / "kernels" / "dispositions"
+    d.mkdir(parents=True)
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex 15\nproperty float64 x\nproperty float64 y\n"
+              "property float64 z\nend_header\n").encode()
+    (d / "k_015_center_3D.ply").write_bytes(header + pts.astype("<f8").tobytes())
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(3)
+    got = load_kernels(2.0, 15, 3, "center")
+    np.random.seed(3)
+    theta = np.random.rand() * 2 * np.pi
+    c, s = np.cos(theta), np.sin(theta)
+    rot = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], dtype=np.float32)
+    want = np.matmul(2.0 * (pts + np.random.normal(scale=0.01, size=pts.shape)), rot).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_segment_instance_norm_matches_torch_instance_norm():
+    torch.manual_seed(0)
+    lens = torch.tensor([37, 1200, 5], dtype=torch.int32)
+    x = torch.randn(int(lens.sum()), 24) * 3 + 1
+    got = _segment_instance_norm(x, lens)
+    norm = torch.nn.InstanceNorm1d(24, momentum=0.02)
+    want = torch.cat([norm(seg.t().unsqueeze(0)).squeeze(0).t() for seg in torch.split(x, lens.tolist())], 0)
+    assert rel_err(got.numpy(), want.numpy()) < 1e-5
+
+
+def test_synthetic_clouds_have_the_baseline_shapes():
+    src, tgt, pose = synthetic.threedmatch_pair(seed=0)
+    assert 15000 < len(src) < 26000 and 15000 < len(tgt) < 26000 and pose.shape == (3, 4)
+    assert np.allclose(pose[:, :3] @ pose[:, :3].T, np.eye(3), atol=1e-5)
+    s2, _, _ = synthetic.threedmatch_pair(seed=0)
+    assert np.array_equal(src, s2)  # seeded
+    src, tgt, _ = synthetic.modelnet_pair(seed=0)
+    assert src.shape == (717, 3) and np.abs(src).max() <= 1.1
+
+
+def test_shard_pairs_round_robin():
+    shards = [shard_pairs(10, r, 4) for r in range(4)]
+    assert shards == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    assert sorted(sum(shards, [])) == list(range(10))
