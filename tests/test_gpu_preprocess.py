@@ -71,6 +71,8 @@ def test_batch_query_bit_exact(oracle, seed, ql, sl, r):
     ql, sl = np.array(ql, np.int32), np.array(sl, np.int32)
     q = rng.uniform(-1, 1, size=(int(ql.sum()), 3)).astype(np.float32)
     s = rng.uniform(-1, 1, size=(int(sl.sum()), 3)).astype(np.float32)
+    if len(q) == 1:
+        s[0] = q[0] + np.float32(0.01)  # a lone query must have a neighbour (an empty result raises, as in the reference)
     want, ties = oracle.batch_query(q, s, ql, sl, r, impl="port", return_ties=True)
     got = cpp_neighbors.batch_query(q, s, ql, sl, radius=r)
     assert got.dtype == np.int32
@@ -119,7 +121,7 @@ def test_batch_query_properties_full_size():
     padded = np.concatenate([pts, np.full((1, 3), 1e6, np.float32)])
     d = np.linalg.norm(padded[nb] - pts[:, None, :], axis=2)
     assert (d[valid] < r * (1 + 1e-6)).all()
-    dd = np.where(valid, d, np.inf)
+    dd = np.where(valid, d, np.float32(1e3) + np.arange(nb.shape[1], dtype=np.float32)[None, :])
     assert (np.diff(dd, axis=1) >= -1e-7).all()
     rows = np.repeat(np.arange(n), nb.shape[1])[valid.ravel()]
     cols = nb.ravel()[valid.ravel()]
