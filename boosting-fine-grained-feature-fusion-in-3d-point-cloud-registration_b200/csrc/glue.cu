@@ -1,0 +1,227 @@
+// Encoder-block glue on sm_100a: the dense layers and per-cloud normalisation that
+// sit around KPConv inside the reference's blocks.
+//
+//   kpreg_linear_forward        y = act((x W^T) * col_scale + col_shift + residual)
+//       replaces nn.Linear(bias=False) [+ eval-mode nn.BatchNorm1d folded into col_scale/col_shift] [+ ReLU]
+//       of UnaryBlock.mlp (reference finegrained_kpconv_blocks.py:521-555) and of my_Bottle2neck's
+//       conv1/bn1, convs[i]/bns[i], conv3/bn3, downsample (reference res2net.py:84-159, 231-265);
+//       runs on the tcgen05 3xTF32 GEMM of kpconv_gemm.cu (fp32-grade accuracy), fp32 CUDA cores otherwise.
+//   kpreg_segment_norm_forward  y = act((x - mean_c) * rstd_c + residual) per cloud c and channel
+//       replaces BatchNormBlock's per-cloud nn.InstanceNorm1d (affine=False, eps 1e-5, biased variance;
+//       reference finegrained_kpconv_blocks.py:462-518, a Python loop over clouds there), optionally fused
+//       with the LeakyReLU / shortcut-add that follows it (:552-554, :632-634, :712-725).
+#include "common.cuh"
+
+namespace kpreg {
+
+int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
+                   const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
+                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, cudaStream_t stream);
+int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
+size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
+bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
+
+namespace {
+
+__device__ __forceinline__ float activate(float x, int act, float slope) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return x > 0.f ? x : x * slope;
+  return x;
+}
+
+// fp32 CUDA-core fallback: one thread per output element (shapes the TMA path cannot address are tiny).
+__global__ void __launch_bounds__(256) k_linear_simple(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                       int64_t m_rows, int k_dim, int n_dim, const float* __restrict__ col_scale,
+                                                       const float* __restrict__ col_shift, const float* __restrict__ residual,
+                                                       int ld_res, int act, float slope, float* __restrict__ out, int ldc,
+                                                       float* __restrict__ out2, int ld2, const float* __restrict__ addend,
+                                                       int ld_add) {
+  const int64_t total = m_rows * (int64_t)n_dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / n_dim;
+    const int n = (int)(i - m * n_dim);
+    float acc = 0.f;
+    for (int k = 0; k < k_dim; ++k) acc = fmaf(x[m * ldx + k], w[(int64_t)n * k_dim + k], acc);
+    if (col_scale) acc *= col_scale[n];
+    if (col_shift) acc += col_shift[n];
+    if (residual) acc += residual[m * ld_res + n];
+    acc = activate(acc, act, slope);
+    out[m * ldc + n] = acc;
+    if (out2) out2[m * ld2 + n] = acc + addend[m * ld_add + n];
+  }
+}
+
+constexpr int kStatRows = 128;  // rows per CTA
+constexpr int kStatCh = 64;     // channels per CTA (threadIdx.x & 63), 4 row groups
+
+// stats[(cloud * C + ch) * 2 + {0,1}] += {sum x, sum x^2} in fp64
+__global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
+                                                       int n_clouds, int64_t n_rows, int channels, double* __restrict__ stats) {
+  __shared__ double s_sum[4][kStatCh], s_sq[4][kStatCh];
+  const int cx = threadIdx.x & (kStatCh - 1), ry = threadIdx.x >> 6;
+  const int ch = blockIdx.y * kStatCh + cx;
+  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
+  const int64_t r1 = min(n_rows, r0 + kStatRows);
+  const int c_first = cloud_of(off, n_clouds, r0);
+  const int c_last = cloud_of(off, n_clouds, r1 - 1);
+  const bool live = ch < channels;
+  if (c_first == c_last) {
+    double sum = 0.0, sq = 0.0;
+    if (live)
+      for (int64_t r = r0 + ry; r < r1; r += 4) {
+        const double v = (double)x[r * ldx + ch];
+        sum += v;
+        sq += v * v;
+      }
+    s_sum[ry][cx] = sum;
+    s_sq[ry][cx] = sq;
+    __syncthreads();
+    if (ry == 0 && live) {
+      sum = s_sum[0][cx] + s_sum[1][cx] + s_sum[2][cx] + s_sum[3][cx];
+      sq = s_sq[0][cx] + s_sq[1][cx] + s_sq[2][cx] + s_sq[3][cx];
+      double* dst = stats + ((int64_t)c_first * channels + ch) * 2;
+      atomicAdd(dst, sum);
+      atomicAdd(dst + 1, sq);
+    }
+  } else if (live) {
+    // chunk straddles a cloud boundary: flush per thread whenever the cloud changes
+    int c = -1;
+    double sum = 0.0, sq = 0.0;
+    for (int64_t r = r0 + ry; r < r1; r += 4) {
+      const int cr = cloud_of(off, n_clouds, r);
+      if (cr != c) {
+        if (c >= 0) {
+          double* dst = stats + ((int64_t)c * channels + ch) * 2;
+          atomicAdd(dst, sum);
+          atomicAdd(dst + 1, sq);
+        }
+        c = cr;
+        sum = sq = 0.0;
+      }
+      const double v = (double)x[r * ldx + ch];
+      sum += v;
+      sq += v * v;
+    }
+    if (c >= 0) {
+      double* dst = stats + ((int64_t)c * channels + ch) * 2;
+      atomicAdd(dst, sum);
+      atomicAdd(dst + 1, sq);
+    }
+  }
+}
+
+// mean / rstd per (cloud, channel) from the fp64 moments: biased variance, eps inside the sqrt.
+__global__ void __launch_bounds__(256) k_segnorm_finalize(const double* __restrict__ stats, const int64_t* __restrict__ off,
+                                                          int n_clouds, int channels, float eps, float2* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_clouds * channels) return;
+  const int c = i / channels;
+  const double n = (double)max((int64_t)1, off[c + 1] - off[c]);
+  const double mean = stats[2 * i] / n;
+  double var = stats[2 * i + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+__global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
+                                                       int n_clouds, int64_t n_rows, int channels, const float2* __restrict__ mr,
+                                                       const float* __restrict__ residual, int ld_res, int act, float slope,
+                                                       float* __restrict__ out, int ldo) {
+  const int c4 = channels >> 2;
+  const int64_t total = n_rows * (int64_t)c4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int ch = (int)(i - r * c4) * 4;
+    const int c = cloud_of(off, n_clouds, r);
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+    const float2* m = mr + (int64_t)c * channels + ch;
+    const float2 m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+    float4 y = make_float4((v.x - m0.x) * m0.y, (v.y - m1.x) * m1.y, (v.z - m2.x) * m2.y, (v.w - m3.x) * m3.y);
+    if (residual) {
+      const float4 q = *reinterpret_cast<const float4*>(residual + r * ld_res + ch);
+      y.x += q.x; y.y += q.y; y.z += q.z; y.w += q.w;
+    }
+    y.x = activate(y.x, act, slope); y.y = activate(y.y, act, slope);
+    y.z = activate(y.z, act, slope); y.w = activate(y.w, act, slope);
+    *reinterpret_cast<float4*>(out + r * ldo + ch) = y;
+  }
+}
+
+struct NormWs { int64_t* off; double* stats; float2* mr; size_t total; };
+NormWs carve_norm(void* base, int n_clouds, int channels) {
+  NormWs w;
+  Carver cv(base);
+  w.off = cv.take<int64_t>((size_t)n_clouds + 1);
+  w.stats = cv.take<double>((size_t)n_clouds * channels * 2);
+  w.mr = cv.take<float2>((size_t)n_clouds * channels);
+  w.total = align_up(cv.used, 256);
+  return w;
+}
+
+}  // namespace
+}  // namespace kpreg
+
+using namespace kpreg;
+
+extern "C" int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes) {
+  if (!bytes || k_dim < 1 || n_dim < 1) return KPREG_E_INVALID;
+  *bytes = kpconv_gemm_tc_weight_bytes(k_dim, n_dim) + 256;
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
+                                    const float* col_scale, const float* col_shift, const float* residual, int ld_res, int act,
+                                    float slope, float* out, int ldc, float* out2, int ld2, const float* addend, int ld_add,
+                                    int gemm, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (m_rows < 0 || k_dim < 1 || n_dim < 1 || ldx < k_dim || ldc < n_dim || act < 0 || act > 2) return KPREG_E_INVALID;
+  if (m_rows == 0) return KPREG_OK;
+  if (!x || !weight || !out || (out2 && !addend)) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ProfScope prof(KPREG_FAM_LINEAR, stream);
+  if (gemm == 1 && gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x)) {
+    if (!workspace || workspace_bytes < kpconv_gemm_tc_weight_bytes(k_dim, n_dim)) return KPREG_E_WORKSPACE;
+    float* w_split = static_cast<float*>(workspace);
+    int rc = kpconv_gemm_tc_prepare_weights(weight, k_dim, n_dim, 0, w_split, stream);
+    if (rc) return rc;
+    return launch_gemm_tc(x, ldx, w_split, out, ldc, m_rows, k_dim, n_dim, nullptr, col_scale, col_shift, residual, ld_res, act,
+                          slope, out2, ld2, addend, ld_add, stream);
+  }
+  int blocks = ceil_div(m_rows * (int64_t)n_dim, 256);
+  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  k_linear_simple<<<blocks, 256, 0, stream>>>(x, ldx, weight, m_rows, k_dim, n_dim, col_scale, col_shift, residual, ld_res, act,
+                                              slope, out, ldc, out2, ld2, addend, ld_add);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes) {
+  if (!bytes || n_clouds < 1 || channels < 1) return KPREG_E_INVALID;
+  *bytes = carve_norm(nullptr, n_clouds, channels).total;
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
+                                          int channels, float eps, const float* residual, int ld_res, int act, float slope,
+                                          float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (n_rows < 0 || n_clouds < 1 || channels < 4 || (channels & 3) || (ldx & 3) || (ldo & 3) || act < 0 || act > 2) return KPREG_E_INVALID;
+  if (residual && (ld_res & 3)) return KPREG_E_INVALID;
+  if (n_rows == 0) return KPREG_OK;
+  if (!x || !lens || !out || !workspace) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NormWs w = carve_norm(workspace, n_clouds, channels);
+  if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
+  ProfScope prof(KPREG_FAM_NORM, stream);
+  int rc = launch_cloud_offsets(lens, n_clouds, w.off, stream);
+  if (rc) return rc;
+  KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
+  dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
+  k_segnorm_stats<<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  KP_LAUNCH_CHECK();
+  k_segnorm_finalize<<<ceil_div((int64_t)n_clouds * channels, 256), 256, 0, stream>>>(w.stats, w.off, n_clouds, channels, eps, w.mr);
+  KP_LAUNCH_CHECK();
+  int blocks = ceil_div(n_rows * (int64_t)(channels >> 2), 256);
+  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  k_segnorm_apply<<<blocks, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.mr, residual, ld_res, act, slope, out, ldo);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}

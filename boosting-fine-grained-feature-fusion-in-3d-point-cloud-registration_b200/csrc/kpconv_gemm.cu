@@ -1,6 +1,405 @@
+// fp32-accurate tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, fed by TMA.
+//
+//   C[M,N] = epilogue( A[M,K] * B^T ),   A row-major [M,K] fp32,  B given K-major as Bt[N,K]
+//
+// This is the one dense contraction of the KPConv path — the [n_q, K*c_in] x [K*c_in, c_out] product
+// of KPConv.forward (reference models/backbone_kpconv/finegrained_kpconv_blocks.py:388-393) — and the
+// same kernel serves the Linear layers of the encoder blocks.
+//
+// Precision.  The reference computes in fp32 and parity is 1e-4 relative, which a single TF32 pass
+// (10-bit mantissa) does not meet.  Every fp32 operand is therefore split x = hi + lo with
+// hi = x & 0xffffe000 (exactly representable in TF32) and lo = x - hi (exact in fp32), and the product is
+// accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32; the dropped lo*lo term is
+// ~2^-22 relative).  B (the weights) is split once per call by k_split_weights; A is split on the fly in
+// shared memory by the CTA's four "splitter" warps, so A crosses HBM once, as plain fp32.
+//
+// CTA = 192 threads, one 128 x BLOCK_N output tile, K in blocks of 32 floats (one 128-byte swizzle row):
+//   warp 0    TMA producer: per stage one box of A (128 x 32) and two of Bt (BLOCK_N x 32: hi, lo),
+//             SWIZZLE_128B, completion on full[stage]
+//   warp 1    TMEM allocation; one elected lane issues 12 tcgen05.mma per stage (4 k-steps x 3 products),
+//             tcgen05.commit frees the stage (empty[stage]) and finally signals tmem_full
+//   warps 2-5 splitters: wait full[stage], rewrite the A box in place as hi and write lo to a second
+//             box (element-wise, so swizzle-agnostic), fence.proxy.async, arrive on split_done[stage];
+//             afterwards the same warps are the epilogue: tcgen05.ld their 32 TMEM lanes, apply
+//             row scale / column scale+shift / residual / activation, vectorised global stores.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace kpreg {
-size_t kpconv_gemm_tc_weight_bytes(int kd, int n) { return 256; }
-int kpconv_gemm_tc_prepare_weights(const float*, int, int, float*, cudaStream_t) { return KPREG_E_INVALID; }
-int launch_kpconv_gemm_tc(const float*, const float*, const float*, float*, int64_t, int, int, void*, cudaStream_t) { return KPREG_E_INVALID; }
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;          // floats per 128-byte swizzle row
+constexpr int UMMA_K = 8;            // tf32
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart, version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, shape M x N x 8.
+__device__ __forceinline__ uint32_t make_instr_desc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Epilogue {
+  const float* row_scale;  // [M] or null
+  const float* col_scale;  // [N] or null
+  const float* col_shift;  // [N] or null
+  const float* residual;   // [M, ld_res] or null, added before the activation
+  int ld_res;
+  int act;                 // 0 none, 1 relu, 2 leaky relu (slope below)
+  float slope;
+  float* out2;             // optional second output [M, ld2] = C + addend (the next chained layer's input)
+  const float* addend;     // [M, ld_add]
+  int ld2, ld_add;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr uint32_t kStageBytes = 2 * kABoxBytes + 2 * kBBoxBytes;
+  static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
+  static constexpr uint32_t kBarrierBytes = 256;
+  static constexpr uint32_t kTotal = kTileBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+                                                          const __grid_constant__ CUtensorMap map_b_hi,
+                                                          const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C,
+                                                          int64_t M, int N, int K, int ldc, Epilogue ep) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // stage s: [A hi (TMA lands raw A here) | A lo | B hi | B lo]
+  const uint32_t bar_base = base + L::kTileBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + L::kTileBytes + 8u * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BLOCK_N < 32 ? 32 : BLOCK_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t round = (uint32_t)(kb / STAGES);
+        mbar_wait(empty_bar(s), (round & 1u) ^ 1u);
+        const uint32_t st = base + (uint32_t)s * L::kStageBytes;
+        mbar_expect_tx(full_bar(s), kABoxBytes + 2 * L::kBBoxBytes);
+        tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, (int)m0);
+        tma_load_2d(st + 2 * kABoxBytes, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
+        tma_load_2d(st + 2 * kABoxBytes + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t round = (uint32_t)(kb / STAGES);
+        mbar_wait(split_bar(s), round & 1u);
+        tcgen05_fence_after();
+        const uint32_t st = base + (uint32_t)s * L::kStageBytes;
+        const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kABoxBytes);
+        const uint64_t b_hi = make_smem_desc(st + 2 * kABoxBytes), b_lo = make_smem_desc(st + 2 * kABoxBytes + L::kBBoxBytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step inside the swizzle row
+          umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ---------------- splitters (warps 2..5), then epilogue
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t round = (uint32_t)(kb / STAGES);
+      mbar_wait(full_bar(s), round & 1u);
+      float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes + kABoxBytes);
+#pragma unroll
+      for (int j = 0; j < (int)(kABoxBytes / 16) / 128; ++j) {
+        const int i = t + 128 * j;
+        const float4 v = hi[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        hi[i] = h;
+        lo[i] = l;
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split_bar(s));
+    }
+    // epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31 = output rows
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row_in_tile = 32 * (warp & 3) + lane;
+    const int64_t m = m0 + row_in_tile;
+    const float rs = (ep.row_scale != nullptr && m < M) ? ep.row_scale[m] : 1.0f;
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, r);
+      if (m < M) {
+        float* __restrict__ crow = C + m * (int64_t)ldc;
+        const float* __restrict__ rrow = ep.residual ? ep.residual + m * (int64_t)ep.ld_res : nullptr;
+        float* __restrict__ orow = ep.out2 ? ep.out2 + m * (int64_t)ep.ld2 : nullptr;
+        const float* __restrict__ arow = ep.out2 ? ep.addend + m * (int64_t)ep.ld_add : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n >= N) break;
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int nn = n + q;
+            float x = __uint_as_float(r[j + q]) * rs;
+            if (nn < N) {
+              if (ep.col_scale) x *= ep.col_scale[nn];
+              if (ep.col_shift) x += ep.col_shift[nn];
+              if (rrow) x += rrow[nn];
+            }
+            if (ep.act == 1) x = fmaxf(x, 0.f);
+            else if (ep.act == 2) x = x > 0.f ? x : x * ep.slope;
+            v[q] = x;
+          }
+          if (n + 3 < N && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (n + q < N) crow[n + q] = v[q];
+          }
+          if (orow) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (n + q < N) orow[n + q] = v[q] + arow[n + q];
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BLOCK_N < 32 ? 32 : BLOCK_N));
+  }
+}
+
+// Bt_hi / Bt_lo [N, ldb] (K-major) from W: either [K, N] row-major (transpose = 1, the KPConv weights
+// flattened to [K*c_in, c_out]) or [N, K] row-major (transpose = 0, an nn.Linear weight).
+__global__ void __launch_bounds__(256) k_split_weights(const float* __restrict__ w, int k_dim, int n_dim, int ldb, int transpose,
+                                                       float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = (int64_t)n_dim * ldb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ldb), k = (int)(i - (int64_t)n * ldb);
+    float v = 0.f;
+    if (k < k_dim) v = transpose ? w[(int64_t)k * n_dim + n] : w[(int64_t)n * k_dim + k];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (floats), box = [box_rows, 32 floats], SWIZZLE_128B.
+int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return KPREG_E_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
+    return KPREG_E_CUDA;
+  }
+  return KPREG_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, float* C, int64_t M, int N, int K,
+                       int ldc, const Epilogue& ep, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(M, BLOCK_M), (unsigned)ceil_div(N, BLOCK_N));
+  k_gemm_tc<BLOCK_N, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, C, M, N, K, ldc, ep);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+int ldb_for(int k_dim) { return (k_dim + 3) / 4 * 4; }
+int npad_for(int n_dim) { return (n_dim + 15) / 16 * 16; }
+
+}  // namespace
+
+size_t kpconv_gemm_tc_weight_bytes(int kd, int n) {
+  // hi and lo copies of Bt [npad, ldb]
+  return align_up((size_t)2 * (size_t)npad_for(n) * (size_t)ldb_for(kd) * sizeof(float) + 512, 256);
+}
+
+bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a) {
+  return m > 0 && kd >= 4 && (lda % 4) == 0 && n >= 8 && (reinterpret_cast<uintptr_t>(a) % 16) == 0;
+}
+
+// Split the weights: w is [kd, n] (transpose = 1) or [n, kd] (transpose = 0).  w_split holds hi then lo.
+int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream) {
+  const int ldb = ldb_for(kd);
+  float* hi = w_split;
+  float* lo = w_split + (size_t)npad_for(n) * ldb;
+  const int64_t total = (int64_t)n * ldb;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  k_split_weights<<<blocks, 256, 0, stream>>>(weights, kd, n, ldb, transpose, hi, lo);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+// C[m, n] (row pitch ldc) = epilogue(A[m, kd] (row pitch lda) * Bt^T) with pre-split weights.
+int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
+                   const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
+                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, cudaStream_t stream) {
+  if (!gemm_tc_supported(m, kd, n, lda, a)) return KPREG_E_INVALID;
+  const int ldb = ldb_for(kd);
+  const float* hi = w_split;
+  const float* lo = w_split + (size_t)npad_for(n) * ldb;
+  const int block_n = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
+  CUtensorMap ma, mbh, mbl;
+  int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mbh, hi, n, kd, ldb, block_n);
+  if (rc) return rc;
+  rc = make_map(&mbl, lo, n, kd, ldb, block_n);
+  if (rc) return rc;
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add};
+  if (block_n == 32) return launch_tile_config<32, 2>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 2>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 3>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+}
+
+}  // namespace kpreg

@@ -56,7 +56,9 @@ KPREG_API unsigned long long kpreg_launch_count(void);
 #define KPREG_FAM_POOL 5        /* k_max_pool */
 #define KPREG_FAM_KABSCH 6      /* k_kabsch */
 #define KPREG_FAM_OTHER 7       /* pack rows, row sums, backward kernels */
-#define KPREG_N_FAMILIES 8
+#define KPREG_FAM_LINEAR 8      /* kpreg_linear_forward */
+#define KPREG_FAM_NORM 9        /* kpreg_segment_norm_forward */
+#define KPREG_N_FAMILIES 10
 KPREG_API int kpreg_profile(int enable);
 KPREG_API int kpreg_profile_read(double* ms /*[KPREG_N_FAMILIES]*/, unsigned long long* launches /*[KPREG_N_FAMILIES]*/);
 
@@ -155,6 +157,32 @@ KPREG_API int kpreg_max_pool_backward(const float* grad_out, const int32_t* argm
  * ------------------------------------------------------------------------------------------- */
 KPREG_API int kpreg_kabsch(const float* a, const float* b, float* w, const int64_t* offsets, int64_t n_sets,
                  int64_t pts_per_set, float threshold, int write_back, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encoder-block glue (the step around KPConv inside every block).
+ *
+ * kpreg_linear_forward: out[m, n] = act( (sum_k x[m,k] * weight[n,k]) * col_scale[n] + col_shift[n] + residual[m,n] )
+ *   Replaces nn.Linear(bias=False) of UnaryBlock.mlp (models/backbone_kpconv/finegrained_kpconv_blocks.py:521-555)
+ *   and of my_Bottle2neck (models/backbone_kpconv/res2net.py:84-159), with an eval-mode BatchNorm1d folded into
+ *   col_scale / col_shift and the following ReLU in `act` (0 none, 1 relu, 2 leaky relu with `slope`).
+ *   x [M, ldx], weight [N, K] (nn.Linear layout), out [M, ldc]; col_scale / col_shift / residual may be NULL.
+ *   out2 (optional) [M, ld2] receives out + addend[M, ld_add] — the input of the next layer of res2net's chain.
+ *   gemm: 1 = tcgen05 3xTF32 (falls back when the shape is not TMA-addressable), 0 = fp32 CUDA cores.
+ *
+ * kpreg_segment_norm_forward: out = act( (x - mean[c]) * rstd[c] + residual ), statistics per cloud c and channel
+ *   Replaces BatchNormBlock's per-cloud nn.InstanceNorm1d (finegrained_kpconv_blocks.py:462-518; biased variance,
+ *   eps inside the square root, no affine, no running statistics), optionally fused with the activation and the
+ *   shortcut addition that follow it in the blocks.  channels, ldx, ldo, ld_res must be multiples of 4.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes);
+KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
+                                   const float* col_scale, const float* col_shift, const float* residual, int ld_res,
+                                   int act, float slope, float* out, int ldc, float* out2, int ld2, const float* addend,
+                                   int ld_add, int gemm, void* workspace, size_t workspace_bytes, void* stream);
+KPREG_API int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes);
+KPREG_API int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
+                                         int channels, float eps, const float* residual, int ld_res, int act, float slope,
+                                         float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
