@@ -45,6 +45,12 @@ _SIGNATURES = {
     "kpreg_max_pool_forward": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr,
                                         _c_ptr]),
     "kpreg_max_pool_backward": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_int, _c_ptr, _c_ptr]),
+    "kpreg_linear_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_linear_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int,
+                                      _c_f32, _c_ptr, _c_int, _c_ptr, _c_int, _c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_segment_norm_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_segment_norm_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
+                                            _c_f32, _c_ptr, _c_int, _c_ptr, _c_size, _c_ptr]),
     "kpreg_kabsch": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f32, _c_int, _c_ptr, _c_ptr]),
 }
 
@@ -97,7 +103,8 @@ def launch_count() -> int:
     return int(load().kpreg_launch_count())
 
 
-FAMILIES = ("subsample", "grid_build", "grid_query", "kpconv_gather", "kpconv_contract", "max_pool", "kabsch", "other")
+FAMILIES = ("subsample", "grid_build", "grid_query", "kpconv_gather", "kpconv_contract", "max_pool", "kabsch", "other",
+            "linear", "segment_norm")
 
 
 def profile(enable: bool) -> None:

@@ -8,20 +8,21 @@
 //
 // Precision.  The reference computes in fp32 and parity is 1e-4 relative, which a single TF32 pass
 // (10-bit mantissa) does not meet.  Every fp32 operand is therefore split x = hi + lo with
-// hi = x & 0xffffe000 (exactly representable in TF32) and lo = x - hi (exact in fp32), and the product is
-// accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32; the dropped lo*lo term is
-// ~2^-22 relative).  B (the weights) is split once per call by k_split_weights; A is split on the fly in
+// hi = rn_tf32(x) and lo = rn_tf32(x - hi) (cvt.rna.tf32.f32; x - hi is exact in fp32), and the product is
+// accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32; what is dropped — lo*lo and
+// the rounding of lo — is ~2^-22 relative and unbiased).  B (the weights) is split once per call by k_split_weights; A is split on the fly in
 // shared memory by the CTA's four "splitter" warps, so A crosses HBM once, as plain fp32.
 //
-// CTA = 192 threads, one 128 x BLOCK_N output tile, K in blocks of 32 floats (one 128-byte swizzle row):
+// Persistent CTA = 320 threads, 128 x BLOCK_N output tiles, K in blocks of 32 floats (one 128-byte swizzle row):
 //   warp 0    TMA producer: per stage one box of A (128 x 32) and two of Bt (BLOCK_N x 32: hi, lo),
-//             SWIZZLE_128B, completion on full[stage]
+//             SWIZZLE_128B, completion on full[stage]; runs ahead across tile boundaries
 //   warp 1    TMEM allocation; one elected lane issues 12 tcgen05.mma per stage (4 k-steps x 3 products),
-//             tcgen05.commit frees the stage (empty[stage]) and finally signals tmem_full
+//             tcgen05.commit frees the stage (empty[stage]) and signals tmem_full[buffer] per tile
 //   warps 2-5 splitters: wait full[stage], rewrite the A box in place as hi and write lo to a second
-//             box (element-wise, so swizzle-agnostic), fence.proxy.async, arrive on split_done[stage];
-//             afterwards the same warps are the epilogue: tcgen05.ld their 32 TMEM lanes, apply
-//             row scale / column scale+shift / residual / activation, vectorised global stores.
+//             box (element-wise, so swizzle-agnostic), fence.proxy.async, arrive on split_done[stage]
+//   warps 6-9 epilogue: tcgen05.ld their 32 TMEM lanes from the finished accumulator buffer, release it
+//             (tmem_empty[buffer]), transpose through shared memory and apply row scale / column scale+shift /
+//             residual / activation with coalesced global accesses — while the next tile's MMAs run.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,7 +33,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;          // floats per 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -106,6 +107,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// x = hi + lo with hi = x rounded to nearest TF32 and lo = (x - hi) rounded to nearest TF32 (x - hi is exact in
+// fp32); both are exactly representable, so the tensor core's own fp32->tf32 conversion changes nothing.
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_round(x);
+  lo = tf32_round(x - hi);
+}
+
 struct Epilogue {
   const float* row_scale;  // [M] or null
   const float* col_scale;  // [N] or null
@@ -117,38 +130,55 @@ struct Epilogue {
   float* out2;             // optional second output [M, ld2] = C + addend (the next chained layer's input)
   const float* addend;     // [M, ld_add]
   int ld2, ld_add;
+  int vec_ok;              // every row pointer (C, residual, out2, addend) is 16-byte aligned: float4 accesses allowed
 };
 
-template <int BLOCK_N, int STAGES>
+// TMEM accumulators per tile: NUM_HI for the hi*hi products (round-robin over k-steps) + 1 for the cross terms.
+template <int BLOCK_N, int NUM_HI, int STAGES>
 struct SmemLayout {
+  static constexpr int kNumAcc = NUM_HI + 1;
   static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
   static constexpr uint32_t kStageBytes = 2 * kABoxBytes + 2 * kBBoxBytes;
   static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
+  static constexpr uint32_t kEpiBytes = 4 * 2 * BLOCK_N * 4;  // per epilogue warp: column scale and shift of the tile
   static constexpr uint32_t kBarrierBytes = 256;
-  static constexpr uint32_t kTotal = kTileBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
+  static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
+  static constexpr uint32_t kTmemCols = 2 * kNumAcc * BLOCK_N;  // double-buffered accumulators
+  static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
 };
 
-template <int BLOCK_N, int STAGES>
+// Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
+// tile = blockIdx.x + i * gridDim.x, (m_blk, n_blk) = (tile / num_n, tile % num_n).  The shared-memory ring and
+// its phases run on across tiles, and the accumulators are double-buffered in TMEM, so TMA prefetch, operand
+// splitting, MMA issue and the epilogue of consecutive tiles overlap.
+//
+// Accuracy note: tcgen05 adds each 8-deep product into the fp32 accumulator with truncation, a bias that grows
+// with the number of accumulation steps (measured 3e-5 relative at K = 3840 with a single accumulator).  The
+// (2^-11 smaller) cross terms therefore get their own accumulator, and for long K the hi*hi products of
+// consecutive k-steps rotate over three accumulators; the epilogue adds them in fp32 round-to-nearest.
+template <int BLOCK_N, int NUM_HI, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C,
                                                           int64_t M, int N, int K, int ldc, Epilogue ep) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
+  constexpr int kNumAcc = L::kNumAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   // stage s: [A hi (TMA lands raw A here) | A lo | B hi | B lo]
-  const uint32_t bar_base = base + L::kTileBytes;
+  const uint32_t bar_base = base + L::kTileBytes + L::kEpiBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + L::kTileBytes + 8u * (3 * STAGES + 1));
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + L::kTileBytes + L::kEpiBytes + 8u * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BLOCK_N;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * num_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -159,133 +189,195 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
       mbar_init(split_bar(s), 4);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BLOCK_N < 32 ? 32 : BLOCK_N));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(L::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ---------------- TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t round = (uint32_t)(kb / STAGES);
-        mbar_wait(empty_bar(s), (round & 1u) ^ 1u);
-        const uint32_t st = base + (uint32_t)s * L::kStageBytes;
-        mbar_expect_tx(full_bar(s), kABoxBytes + 2 * L::kBBoxBytes);
-        tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, (int)m0);
-        tma_load_2d(st + 2 * kABoxBytes, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
-        tma_load_2d(st + 2 * kABoxBytes + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (int)(tile / num_n) * BLOCK_M, n0 = (int)(tile % num_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+          const uint32_t st = base + (uint32_t)s * L::kStageBytes;
+          mbar_expect_tx(full_bar(s), kABoxBytes + 2 * L::kBBoxBytes);
+          tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, m0);
+          tma_load_2d(st + 2 * kABoxBytes, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
+          tma_load_2d(st + 2 * kABoxBytes + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t round = (uint32_t)(kb / STAGES);
-        mbar_wait(split_bar(s), round & 1u);
+      uint32_t it = 0, lt = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u;
+        mbar_wait(tmem_empty_bar(buf), ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator set
         tcgen05_fence_after();
-        const uint32_t st = base + (uint32_t)s * L::kStageBytes;
-        const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kABoxBytes);
-        const uint64_t b_hi = make_smem_desc(st + 2 * kABoxBytes), b_lo = make_smem_desc(st + 2 * kABoxBytes + L::kBBoxBytes);
+        const uint32_t acc0 = tmem_base + buf * (kNumAcc * BLOCK_N);
+        const uint32_t acc_x = acc0 + (uint32_t)NUM_HI * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          mbar_wait(split_bar(s), (it / STAGES) & 1u);
+          tcgen05_fence_after();
+          const uint32_t st = base + (uint32_t)s * L::kStageBytes;
+          const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kABoxBytes);
+          const uint64_t b_hi = make_smem_desc(st + 2 * kABoxBytes), b_lo = make_smem_desc(st + 2 * kABoxBytes + L::kBBoxBytes);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step inside the swizzle row
-          umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step inside the swizzle row
+            const int ks = kb * (BLOCK_K / UMMA_K) + k;
+            umma_tf32(acc_x, a_lo + adv, b_hi + adv, idesc, ks != 0 ? 1u : 0u);
+            umma_tf32(acc_x, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(acc0 + (uint32_t)(ks % NUM_HI) * BLOCK_N, a_hi + adv, b_hi + adv, idesc, ks >= NUM_HI ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
         }
-        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+        umma_commit(tmem_full_bar(buf));  // this tile's accumulators are complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else if (warp < 6) {
+    // ---------------- splitters (warps 2..5)
+    const int t = threadIdx.x - 64;  // 0..127
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = (int)(it % STAGES);
+        mbar_wait(full_bar(s), (it / STAGES) & 1u);
+        float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes);
+        float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes + kABoxBytes);
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = hi[t + 128 * j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 h, l;
+          split_tf32(v[j].x, h.x, l.x);
+          split_tf32(v[j].y, h.y, l.y);
+          split_tf32(v[j].z, h.z, l.z);
+          split_tf32(v[j].w, h.w, l.w);
+          hi[t + 128 * j] = h;
+          lo[t + 128 * j] = l;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(s));
+      }
     }
   } else {
-    // ---------------- splitters (warps 2..5), then epilogue
-    const int t = threadIdx.x - 64;  // 0..127
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t round = (uint32_t)(kb / STAGES);
-      mbar_wait(full_bar(s), round & 1u);
-      float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes);
-      float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes + kABoxBytes);
-#pragma unroll
-      for (int j = 0; j < (int)(kABoxBytes / 16) / 128; ++j) {
-        const int i = t + 128 * j;
-        const float4 v = hi[i];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-        hi[i] = h;
-        lo[i] = l;
+    // ---------------- epilogue (warps 6..9): warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row
+    const int q = warp & 3;
+    float* s_cs = reinterpret_cast<float*>(base_ptr + L::kTileBytes) + q * (2 * BLOCK_N);
+    float* s_cb = s_cs + BLOCK_N;
+    const bool vec_ok = ep.vec_ok != 0;
+    uint32_t lt = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int64_t m = (tile / num_n) * BLOCK_M + 32 * q + lane;
+      const int n0 = (int)(tile % num_n) * BLOCK_N;
+      const uint32_t buf = lt & 1u;
+      // column parameters of this tile -> this warp's shared slice (read back as broadcasts)
+      for (int j = lane; j < BLOCK_N; j += 32) {
+        const int n = n0 + j;
+        s_cs[j] = (ep.col_scale && n < N) ? ep.col_scale[n] : 1.0f;
+        s_cb[j] = (ep.col_shift && n < N) ? ep.col_shift[n] : 0.0f;
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      const float rs = (ep.row_scale && m < M) ? ep.row_scale[m] : 1.0f;
       __syncwarp();
-      if (lane == 0) mbar_arrive(split_bar(s));
-    }
-    // epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31 = output rows
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row_in_tile = 32 * (warp & 3) + lane;
-    const int64_t m = m0 + row_in_tile;
-    const float rs = (ep.row_scale != nullptr && m < M) ? ep.row_scale[m] : 1.0f;
+      mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t acc0 = tmem_base + buf * (kNumAcc * BLOCK_N) + ((uint32_t)(32 * q) << 16);
+      float* __restrict__ crow = C + m * (int64_t)ldc;
+      const float* __restrict__ rrow = ep.residual ? ep.residual + m * (int64_t)ep.ld_res : nullptr;
+      float* __restrict__ orow = ep.out2 ? ep.out2 + m * (int64_t)ep.ld2 : nullptr;
+      const float* __restrict__ arow = ep.out2 ? ep.addend + m * (int64_t)ep.ld_add : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float sum[32];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(acc0 + (uint32_t)c0, r);
 #pragma unroll
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, r);
-      if (m < M) {
-        float* __restrict__ crow = C + m * (int64_t)ldc;
-        const float* __restrict__ rrow = ep.residual ? ep.residual + m * (int64_t)ep.ld_res : nullptr;
-        float* __restrict__ orow = ep.out2 ? ep.out2 + m * (int64_t)ep.ld2 : nullptr;
-        const float* __restrict__ arow = ep.out2 ? ep.addend + m * (int64_t)ep.ld_add : nullptr;
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= N) break;
-          float v[4];
+          for (int a = 1; a < kNumAcc; ++a) {
+            tmem_ld_32x32b_x32(acc0 + (uint32_t)(a * BLOCK_N + c0), r);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int nn = n + q;
-            float x = __uint_as_float(r[j + q]) * rs;
-            if (nn < N) {
-              if (ep.col_scale) x *= ep.col_scale[nn];
-              if (ep.col_shift) x += ep.col_shift[nn];
-              if (rrow) x += rrow[nn];
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+          }
+        }
+        if (c0 + 32 >= BLOCK_N) {
+          // all TMEM reads of this tile are done: hand the accumulator set back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        }
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n >= N) break;
+            const bool full4 = vec_ok && (n + 3 < N);
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = sum[j + e] * rs * s_cs[c0 + j + e] + s_cb[c0 + j + e];
+            if (rrow) {
+              if (full4) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
+                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < N) v[e] += rrow[n + e];
+              }
             }
-            if (ep.act == 1) x = fmaxf(x, 0.f);
-            else if (ep.act == 2) x = x > 0.f ? x : x * ep.slope;
-            v[q] = x;
-          }
-          if (n + 3 < N && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
-            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
+            if (ep.act == 1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (n + q < N) crow[n + q] = v[q];
-          }
-          if (orow) {
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (ep.act == 2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (n + q < N) orow[n + q] = v[q] + arow[n + q];
+              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * ep.slope;
+            }
+            if (full4) {
+              *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < N) crow[n + e] = v[e];
+            }
+            if (orow) {
+              if (full4) {
+                const float4 aa = *reinterpret_cast<const float4*>(arow + n);
+                *reinterpret_cast<float4*>(orow + n) = make_float4(v[0] + aa.x, v[1] + aa.y, v[2] + aa.z, v[3] + aa.w);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < N) orow[n + e] = v[e] + arow[n + e];
+              }
+            }
           }
         }
       }
+      __syncwarp();
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BLOCK_N < 32 ? 32 : BLOCK_N));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::kTmemCols));
   }
 }
 
@@ -298,9 +390,10 @@ __global__ void __launch_bounds__(256) k_split_weights(const float* __restrict__
     const int n = (int)(i / ldb), k = (int)(i - (int64_t)n * ldb);
     float v = 0.f;
     if (k < k_dim) v = transpose ? w[(int64_t)k * n_dim + n] : w[(int64_t)n * k_dim + k];
-    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    float h, l;
+    split_tf32(v, h, l);
     hi[i] = h;
-    lo[i] = v - h;
+    lo[i] = l;
   }
 }
 
@@ -338,17 +431,18 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t
   return KPREG_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int NUM_HI, int STAGES>
 int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, float* C, int64_t M, int N, int K,
                        int ldc, const Epilogue& ep, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
   static bool configured = false;
   if (!configured) {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(M, BLOCK_M), (unsigned)ceil_div(N, BLOCK_N));
-  k_gemm_tc<BLOCK_N, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, C, M, N, K, ldc, ep);
+  const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -388,7 +482,9 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   const int ldb = ldb_for(kd);
   const float* hi = w_split;
   const float* lo = w_split + (size_t)npad_for(n) * ldb;
-  const int block_n = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
+  // long reductions rotate the hi*hi products over three accumulators (see the accuracy note above)
+  const int num_hi = kd > 1024 ? 3 : 1;
+  const int block_n = n <= 32 ? 32 : ((n <= 64 || num_hi == 3) ? 64 : 128);
   CUtensorMap ma, mbh, mbl;
   int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
   if (rc) return rc;
@@ -396,10 +492,16 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   if (rc) return rc;
   rc = make_map(&mbl, lo, n, kd, ldb, block_n);
   if (rc) return rc;
-  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add};
-  if (block_n == 32) return launch_tile_config<32, 2>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
-  if (block_n == 64) return launch_tile_config<64, 2>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
-  return launch_tile_config<128, 3>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  auto aligned = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0); };
+  const int vec_ok = aligned(c, ldc) && aligned(residual, ld_res) && aligned(out2, ld2) && aligned(addend, ld_add);
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok};
+  if (num_hi == 3) {
+    if (block_n == 32) return launch_tile_config<32, 3, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<64, 3, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  }
+  if (block_n == 32) return launch_tile_config<32, 1, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 1, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 1, 3>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
 }
 
 }  // namespace kpreg

@@ -29,7 +29,14 @@ from .kernel_points import load_kernels
 from .res2net import my_Bottle2neck, my_res2Net
 
 # contraction back end used by KPConv.forward: 1 = tcgen05 (3xTF32) tensor-core GEMM, 0 = fp32 CUDA cores
-DEFAULT_GEMM = 0
+DEFAULT_GEMM = 1
+# inference (no autograd) on CUDA: run the blocks' Linear / InstanceNorm / eval-BatchNorm / activation glue on
+# the fused CUDA kernels (kpreg_linear_forward, kpreg_segment_norm_forward); otherwise stock PyTorch ops
+FUSED_GLUE = True
+
+
+def _fused(x: torch.Tensor) -> bool:
+    return FUSED_GLUE and x.is_cuda and not torch.is_grad_enabled()
 
 
 def gather(x, idx, method=2):
@@ -174,10 +181,18 @@ class BatchNormBlock(nn.Module):
     def reset_parameters(self):
         nn.init.zeros_(self.bias)
 
-    def forward(self, x, stack_lengths):
+    def forward(self, x, stack_lengths, act=None, residual=None):
+        """``act`` / ``residual`` let the fused path apply the activation (and shortcut addition) that
+        follows the norm in the same kernel; the default arguments are the reference's signature."""
         if self.use_bn:
-            return _segment_instance_norm(x, stack_lengths)
-        return x + self.bias
+            if _fused(x) and x.shape[1] % 4 == 0:
+                return ops.segment_norm(x, stack_lengths, residual=residual, act=act, slope=0.1)
+            x = _segment_instance_norm(x, stack_lengths)
+        else:
+            x = x + self.bias
+        if residual is not None:
+            x = x + residual
+        return F.leaky_relu(x, 0.1) if act == "leaky_relu" else x
 
     def __repr__(self):
         return 'BatchNormBlock(in_feat: {:d}, momentum: {:.3f}, only_bias: {:s})'.format(
@@ -198,9 +213,17 @@ class UnaryBlock(nn.Module):
         if not no_relu:
             self.leaky_relu = nn.LeakyReLU(0.1)
 
-    def forward(self, x, stack_lengths=None):
+    def forward(self, x, stack_lengths=None, residual=None, final_act=False):
+        """residual / final_act (fused inference only): leaky_relu(norm(mlp(x)) + residual)."""
+        if _fused(x):
+            y = ops.linear_forward(x, self.mlp.weight, gemm=DEFAULT_GEMM)
+            act = "leaky_relu" if (final_act or not self.no_relu) else None
+            return self.batch_norm(y, stack_lengths, act=act, residual=residual)
         x = self.batch_norm(self.mlp(x), stack_lengths)
-        return x if self.no_relu else self.leaky_relu(x)
+        x = x if self.no_relu else self.leaky_relu(x)
+        if residual is not None:
+            x = x + residual
+        return F.leaky_relu(x, 0.1) if final_act else x
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(
@@ -254,7 +277,7 @@ class SimpleBlock(nn.Module):
 
     def forward(self, x, batch):
         q_pts, s_pts, inds, lens = _conv_inputs(batch, self.layer_ind, 'strided' in self.block_name)
-        return self.leaky_relu(self.batch_norm(self.KPConv(q_pts, s_pts, inds, x), lens))
+        return self.batch_norm(self.KPConv(q_pts, s_pts, inds, x), lens, act="leaky_relu")
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -289,7 +312,8 @@ class ResnetBottleneckBlock(nn.Module):
 
         shortcut = max_pool(features, inds) if strided else features
         if isinstance(self.unary_shortcut, UnaryBlock):
-            shortcut = self.unary_shortcut(shortcut, lens_post)
+            # leaky_relu(x + norm(mlp(shortcut))): the addition and activation ride on the norm kernel when fused
+            return self.unary_shortcut(shortcut, lens_post, residual=x, final_act=True)
         return self.leaky_relu(x + shortcut)
 
 

@@ -224,3 +224,74 @@ def kabsch(a: torch.Tensor, b: torch.Tensor, w: Optional[torch.Tensor], n_sets: 
                           float(threshold), 1 if write_back else 0, out.data_ptr(), _lib.stream_ptr(a.device))
     _lib.check(rc, "kpreg_kabsch")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder-block glue: Linear (+ folded BatchNorm + activation) and per-cloud instance norm
+# ------------------------------------------------------------------------------------------------
+
+ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2}
+
+
+def _rows(t: torch.Tensor, name: str):
+    """(tensor, row pitch) of a 2-D fp32 CUDA tensor whose rows are contiguous (column slices are fine)."""
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        t = t.to(torch.float32).contiguous()
+    return t, int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
+def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act=None, slope: float = 0.1, out=None,
+                   out2=None, addend=None, gemm: int = 1):
+    """act((x @ weight.T) * col_scale + col_shift + residual) -> out [M,N] (kpreg_linear_forward).
+    ``out`` may be a column slice of a wider buffer; ``out2`` (optional) receives out + addend."""
+    lib = _lib.load()
+    x, ldx = _rows(x, "x")
+    weight = _f32c(weight, "weight")
+    m, k = x.shape
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise RuntimeError("linear: inconsistent shapes")
+    dev = x.device
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=dev)
+    ldc = int(out.stride(0)) if m > 1 else max(int(out.stride(0)), n)
+    res_ptr, ld_res = None, 0
+    if residual is not None:
+        residual, ld_res = _rows(residual, "residual")
+        res_ptr = residual.data_ptr()
+    o2_ptr, ld2, add_ptr, ld_add = None, 0, None, 0
+    if out2 is not None:
+        addend, ld_add = _rows(addend, "addend")
+        o2_ptr, ld2, add_ptr = out2.data_ptr(), int(out2.stride(0)), addend.data_ptr()
+    cs = None if col_scale is None else _f32c(col_scale, "col_scale")
+    cb = None if col_shift is None else _f32c(col_shift, "col_shift")
+    nbytes = _lib.size_query("kpreg_linear_workspace_bytes", k, n)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_linear_forward(x.data_ptr(), ldx, weight.data_ptr(), m, k, n, _lib.ptr(cs), _lib.ptr(cb), res_ptr, ld_res,
+                                  ACT[act], float(slope), out.data_ptr(), ldc, o2_ptr, ld2, add_ptr, ld_add, int(gemm),
+                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_linear_forward")
+    return out
+
+
+def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: float = 1e-5, out=None):
+    """Per-cloud, per-channel (x - mean) * rstd (+ residual) (+ activation) (kpreg_segment_norm_forward)."""
+    lib = _lib.load()
+    x, ldx = _rows(x, "x")
+    lens = _i32c(lens, "stack_lengths")
+    n, c = x.shape
+    dev = x.device
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    res_ptr, ld_res = None, 0
+    if residual is not None:
+        residual, ld_res = _rows(residual, "residual")
+        res_ptr = residual.data_ptr()
+    nbytes = _lib.size_query("kpreg_segment_norm_workspace_bytes", int(lens.shape[0]), c)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_segment_norm_forward(x.data_ptr(), ldx, lens.data_ptr(), int(lens.shape[0]), n, c, float(eps), res_ptr,
+                                        ld_res, ACT[act], float(slope), out.data_ptr(), int(out.stride(0)) if n > 1 else c,
+                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_segment_norm_forward")
+    return out

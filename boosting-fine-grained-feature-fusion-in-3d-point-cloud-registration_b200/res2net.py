@@ -13,6 +13,20 @@ import torch
 import torch.nn as nn
 
 
+def _folded_bn(bn: nn.BatchNorm1d):
+    """Eval-mode BatchNorm1d as a per-channel (scale, shift), cached until a parameter or statistic changes."""
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+    cache = getattr(bn, "_kpreg_folded", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+        cache = (key, scale.contiguous(), shift.contiguous())
+        bn._kpreg_folded = cache
+    return cache[1], cache[2]
+
+
 class my_Bottle2neck(nn.Module):
     """Linear(in -> w*s) -> split into s groups of width w; group i (i < s-1) is passed through its own
     Linear+BN+ReLU after adding the previous group's output (hierarchical residual); the last group is
@@ -37,7 +51,39 @@ class my_Bottle2neck(nn.Module):
         self.scale = scale
         self.width = width
 
+    def _fused_forward(self, x):
+        """Inference on CUDA: every Linear + eval-BatchNorm + ReLU is one tensor-core GEMM with a fused
+        epilogue; the chain's `previous output + next group` sums are emitted by the producing GEMM."""
+        from . import kpconv_blocks as kb
+        from . import ops
+        w, s = self.width, self.scale
+        gemm = kb.DEFAULT_GEMM
+        sc, sh = _folded_bn(self.bn1)
+        t = ops.linear_forward(x, self.conv1.weight, sc, sh, act="relu", gemm=gemm)          # [N, w*s]
+        cat = torch.empty_like(t)
+        scratch = [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
+        inp = t[:, :w]
+        for i in range(self.nums):
+            sc, sh = _folded_bn(self.bns[i])
+            nxt = i + 1 < self.nums
+            ops.linear_forward(inp, self.convs[i].weight, sc, sh, act="relu", out=cat[:, i * w:(i + 1) * w],
+                               out2=scratch[i & 1] if nxt else None, addend=t[:, (i + 1) * w:(i + 2) * w] if nxt else None,
+                               gemm=gemm)
+            inp = scratch[i & 1]
+        cat[:, self.nums * w:] = t[:, self.nums * w:]
+        residual = x
+        if self.downsample is not None:
+            sc, sh = _folded_bn(self.downsample[1])
+            residual = ops.linear_forward(x, self.downsample[0].weight, sc, sh, gemm=gemm)
+        sc, sh = _folded_bn(self.bn3)
+        return ops.linear_forward(cat, self.conv3.weight, sc, sh, residual=residual, act="relu", gemm=gemm)
+
     def forward(self, x):
+        if (not self.training and x.is_cuda and not torch.is_grad_enabled() and self.stype == 'normal'
+                and self.scale > 1 and self.width % 4 == 0):
+            from . import kpconv_blocks as kb
+            if kb.FUSED_GLUE:
+                return self._fused_forward(x)
         groups = torch.split(self.relu(self.bn1(self.conv1(x))), self.width, 1)
         outs, carry = [], None
         for i in range(self.nums):
