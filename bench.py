@@ -101,7 +101,13 @@ def kpconv_work(meta, cfg):
     n = [int(p.shape[0]) for p in meta["points"]]
     k = cfg.num_kernel_points
     out_dim, in_dim, layer = cfg.first_feats_dim, cfg.in_feats_dim, 0
-    gather_bytes = contract_flops = gather_flops = 0
+    gather_bytes = contract_flops = gather_flops = linear_bytes = linear_flops = norm_bytes = 0
+
+    def lin(m, k_in, n_out):
+        nonlocal linear_bytes, linear_flops
+        linear_bytes += 4 * m * (k_in + n_out) + 4 * k_in * n_out
+        linear_flops += 2 * m * k_in * n_out
+
     for name in cfg.architecture:
         strided = "strided" in name
         if name.startswith("simple"):
@@ -114,6 +120,23 @@ def kpconv_work(meta, cfg):
         gather_bytes += 4 * n_q * h + 12 * (n_s + n_q) + 4 * n_s * c_in + 4 * n_q * c_out + 4 * k * c_in * c_out
         gather_flops += 2 * n_q * k * h * c_in + 12 * n_q * h * k
         contract_flops += 2 * n_q * k * c_in * c_out
+        if name.startswith("simple"):
+            norm_bytes += 8 * n_q * c_out
+        else:
+            # unary1, KPConv norm, res2net (conv1, 7 chained, downsample, conv3), shortcut unary (+ norm)
+            mid, wid = out_dim // 4, int(out_dim * 14 / 64)
+            if in_dim != mid:
+                lin(n_s, in_dim, mid)
+                norm_bytes += 8 * n_s * mid
+            norm_bytes += 8 * n_q * mid
+            lin(n_q, mid, 8 * wid)
+            for _ in range(7):
+                lin(n_q, wid, wid)
+            lin(n_q, mid, out_dim)
+            lin(n_q, 8 * wid, out_dim)
+            if in_dim != out_dim:
+                lin(n_q, in_dim, out_dim)
+                norm_bytes += 12 * n_q * out_dim
         in_dim = out_dim // 2 if name.startswith("simple") else out_dim
         if strided:
             layer += 1
@@ -127,7 +150,8 @@ def kpconv_work(meta, cfg):
             query_bytes += 12 * (n[lvl] + n[lvl + 1]) + 4 * n[lvl] * int(meta["upsamples"][lvl].shape[1])
     sub_bytes = sum(12 * n[l] + 12 * n[l + 1] for l in range(len(n) - 1))
     return {"kpconv_bytes": gather_bytes, "gather_flops": gather_flops, "contract_flops": contract_flops,
-            "query_bytes": query_bytes, "subsample_bytes": sub_bytes}
+            "query_bytes": query_bytes, "subsample_bytes": sub_bytes, "linear_bytes": linear_bytes,
+            "linear_flops": linear_flops, "segment_norm_bytes": norm_bytes}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -206,9 +230,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=16, help="pairs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm", type=int, default=None, help="KPConv contraction: 0 fp32 CUDA cores, 1 tcgen05")
+    ap.add_argument("--gemm", type=int, default=None, help="contractions: 0 fp32 CUDA cores, 1 tcgen05 3xTF32 (default)")
+    ap.add_argument("--no-fused-glue", action="store_true", help="run the block glue on stock PyTorch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -231,9 +256,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 must print exactly one JSON line on stdout: keep NCCL's own banner ("NCCL version ...") off it
+        if "KPREG_KEEP_NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     if args.gemm is not None:
         kpconv_blocks.DEFAULT_GEMM = args.gemm
+    if args.no_fused_glue:
+        kpconv_blocks.FUSED_GLUE = False
 
     cfg = kpconv_config("3dmatch")
     torch.manual_seed(0)
@@ -314,17 +344,31 @@ def main():
         work = kpconv_work(out["meta"], cfg)
         fam_ms = {k: v[0] / args.steps for k, v in fam.items()}
         fam_n = {k: v[1] / args.steps for k, v in fam.items()}
-        top = max(("kpconv_gather", "kpconv_contract", "grid_query", "subsample"), key=lambda k: fam_ms[k])
+        top = max(("kpconv_gather", "kpconv_contract", "grid_query", "subsample", "linear"), key=lambda k: fam_ms[k])
+        nbytes = {"kpconv_gather": work["kpconv_bytes"], "grid_query": work["query_bytes"], "subsample": work["subsample_bytes"],
+                  "linear": work["linear_bytes"], "kpconv_contract": None}[top]
+        names = {"kpconv_gather": "k_kpconv_gather (KPConv gather + influence + aggregation)",
+                 "grid_query": "k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
+                 "linear": "k_gemm_tc (block Linear layers, tcgen05 3xTF32)",
+                 "kpconv_contract": "k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 3xTF32)"}
         if top == "kpconv_contract":
             ach = work["contract_flops"] / (fam_ms[top] * 1e-3) / 1e12
-            roof = {"kernel": "kpconv contraction GEMM [Nq,K*Cin]x[K*Cin,Cout]", "bound": "tensor", "achieved": ach,
-                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None}
+            roof = {"kernel": names[top], "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops"], "traffic": None}
         else:
-            nbytes = {"kpconv_gather": work["kpconv_bytes"], "grid_query": work["query_bytes"],
-                      "subsample": work["subsample_bytes"]}[top]
             ach = nbytes / (fam_ms[top] * 1e-3) / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            roof = {"kernel": names[top], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None}
+        # every family against its own bound, for the record
+        roof["families"] = {
+            "kpconv_gather_GBs": work["kpconv_bytes"] / (fam_ms["kpconv_gather"] * 1e-3) / 1e9,
+            "kpconv_gather_fp32_TFLOPs": work["gather_flops"] / (fam_ms["kpconv_gather"] * 1e-3) / 1e12,
+            "kpconv_contract_TFLOPs": work["contract_flops"] / max(fam_ms["kpconv_contract"], 1e-9) / 1e9,
+            "linear_GBs": work["linear_bytes"] / max(fam_ms["linear"], 1e-9) / 1e6,
+            "linear_TFLOPs": work["linear_flops"] / max(fam_ms["linear"], 1e-9) / 1e9,
+            "grid_query_GBs": work["query_bytes"] / max(fam_ms["grid_query"], 1e-9) / 1e6,
+            "segment_norm_GBs": work["segment_norm_bytes"] / max(fam_ms["segment_norm"], 1e-9) / 1e6,
+        }
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
@@ -354,6 +398,7 @@ def main():
                        "points_per_level": [int(p.shape[0]) for p in out["meta"]["points"]],
                        "neighbor_widths": [int(t.shape[1]) for t in out["meta"]["neighbors"]],
                        "kpconv_contraction": "tcgen05-3xTF32" if kpconv_blocks.DEFAULT_GEMM == 1 else "fp32-cuda-core",
+                       "block_glue": "fused CUDA (tcgen05 linear + segment norm)" if kpconv_blocks.FUSED_GLUE else "PyTorch ops",
                        "parallelism": f"pairs sharded over {world} GPU(s); all-gather of [P,14] poses+errors",
                        "l2": "256 MiB write between timed steps (outside the CUDA events)"},
             "clocks": clocks,
