@@ -30,6 +30,7 @@ bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
 namespace {
 
 constexpr int KMAX = 16;             // kernel points handled per neighbour (reference ships 15)
+constexpr int KSTRIDE = 20;          // floats per neighbour row of influences in shared memory: 16-byte aligned, conflict-free float4 stores
 constexpr int kGatherWarps = 4;      // warps (= queries in flight) per CTA
 
 __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ x, int64_t n_s, int c_in,
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ 
 // Influence of the K kernel points on one neighbour (relative position rx,ry,rz).
 __device__ __forceinline__ void influences(float rx, float ry, float rz, const float* __restrict__ s_kp, int n_kpts,
                                            float extent, int influence, int aggregation, float* __restrict__ w_out) {
+  const float inv_extent = 1.0f / extent;
   float best = 3.4e38f;
   int best_k = 0;
 #pragma unroll
@@ -54,7 +56,7 @@ __device__ __forceinline__ void influences(float rx, float ry, float rz, const f
     if (k < n_kpts) {
       const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
       const float d2 = dx * dx + dy * dy + dz * dz;
-      if (influence == 1) w = fmaxf(1.0f - __fdiv_rn(sqrtf(d2), extent), 0.0f);
+      if (influence == 1) w = fmaxf(1.0f - d2 * rsqrtf(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
       else if (influence == 2) { const float sig = extent * 0.3f; w = expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
       else w = 1.0f;
       if (d2 < best) { best = d2; best_k = k; }
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
     int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num) {
   __shared__ float s_kp[KMAX * 3];
-  __shared__ float s_w[kGatherWarps][32][KMAX + 1];
+  __shared__ __align__(16) float s_w[kGatherWarps][32][KSTRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
         influences(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, s_kp, n_kpts, extent, influence,
                    aggregation, w);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) s_w[warp][lane][k] = w[k];
+        for (int k = 0; k < KMAX; k += 4)
+          *reinterpret_cast<float4*>(&s_w[warp][lane][k]) = make_float4(w[k], w[k + 1], w[k + 2], w[k + 3]);
       }
       num += __popc(__ballot_sync(0xffffffffu, valid && row_pos[j] != 0));
       const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
@@ -114,10 +117,15 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
           xv[cc] = c < c_in ? xr[c] : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const float wk = s_w[warp][hh][k];
+        for (int k = 0; k < KMAX; k += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&s_w[warp][hh][k]);  // broadcast: one wavefront
 #pragma unroll
-          for (int cc = 0; cc < CPL; ++cc) acc[cc][k] = fmaf(wk, xv[cc], acc[cc][k]);
+          for (int cc = 0; cc < CPL; ++cc) {
+            acc[cc][k + 0] = fmaf(w4.x, xv[cc], acc[cc][k + 0]);
+            acc[cc][k + 1] = fmaf(w4.y, xv[cc], acc[cc][k + 1]);
+            acc[cc][k + 2] = fmaf(w4.z, xv[cc], acc[cc][k + 2]);
+            acc[cc][k + 3] = fmaf(w4.w, xv[cc], acc[cc][k + 3]);
+          }
         }
       }
       __syncwarp();
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
     const float* __restrict__ kernel_points, const float* __restrict__ d_agg, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
     int c_in, float extent, int influence, int aggregation, float* __restrict__ d_x) {
   __shared__ float s_kp[KMAX * 3];
-  __shared__ float s_w[kGatherWarps][32][KMAX + 1];
+  __shared__ __align__(16) float s_w[kGatherWarps][32][KSTRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
@@ -169,7 +177,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
         influences(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, s_kp, n_kpts, extent, influence,
                    aggregation, w);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) s_w[warp][lane][k] = w[k];
+        for (int k = 0; k < KMAX; k += 4)
+          *reinterpret_cast<float4*>(&s_w[warp][lane][k]) = make_float4(w[k], w[k + 1], w[k + 2], w[k + 3]);
       }
       const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
       __syncwarp();

@@ -25,6 +25,8 @@
 //             residual / activation with coalesced global accesses — while the next tile's MMAs run.
 #include <cuda.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace kpreg {
@@ -70,6 +72,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -131,6 +140,7 @@ struct Epilogue {
   const float* addend;     // [M, ld_add]
   int ld2, ld_add;
   int vec_ok;              // every row pointer (C, residual, out2, addend) is 16-byte aligned: float4 accesses allowed
+  int tma_store;           // C (and out2) leave through TMA stores from a swizzled shared-memory tile (needs vec_ok)
 };
 
 // TMEM accumulators per tile: NUM_HI for the hi*hi products (round-robin over k-steps) + 1 for the cross terms.
@@ -140,7 +150,8 @@ struct SmemLayout {
   static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
   static constexpr uint32_t kStageBytes = 2 * kABoxBytes + 2 * kBBoxBytes;
   static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
-  static constexpr uint32_t kEpiBytes = 4 * 2 * BLOCK_N * 4;  // per epilogue warp: column scale and shift of the tile
+  static constexpr uint32_t kStoreBytes = 4 * 4096;           // per epilogue warp: one 32 x 32 fp32 tile for TMA stores
+  static constexpr uint32_t kEpiBytes = kStoreBytes + 4 * 2 * BLOCK_N * 4;  // + per warp column scale / shift of the tile
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
   static constexpr uint32_t kTmemCols = 2 * kNumAcc * BLOCK_N;  // double-buffered accumulators
@@ -159,7 +170,9 @@ struct SmemLayout {
 template <int BLOCK_N, int NUM_HI, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
-                                                          const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C,
+                                                          const __grid_constant__ CUtensorMap map_b_lo,
+                                                          const __grid_constant__ CUtensorMap map_c,
+                                                          const __grid_constant__ CUtensorMap map_o2, float* __restrict__ C,
                                                           int64_t M, int N, int K, int ldc, Epilogue ep) {
   using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
   constexpr int kNumAcc = L::kNumAcc;
@@ -283,9 +296,16 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
   } else {
     // ---------------- epilogue (warps 6..9): warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row
     const int q = warp & 3;
-    float* s_cs = reinterpret_cast<float*>(base_ptr + L::kTileBytes) + q * (2 * BLOCK_N);
+    float* s_cs = reinterpret_cast<float*>(base_ptr + L::kTileBytes + L::kStoreBytes) + q * (2 * BLOCK_N);
     float* s_cb = s_cs + BLOCK_N;
+    uint8_t* stg_ptr = base_ptr + L::kTileBytes + q * 4096;  // 1024-byte aligned (SWIZZLE_128B)
+    const uint32_t stg = base + L::kTileBytes + (uint32_t)q * 4096u;
     const bool vec_ok = ep.vec_ok != 0;
+    const bool tma_out = ep.tma_store != 0;
+    if (tma_out && lane == 0) {
+      tma_prefetch_desc(&map_c);
+      if (ep.out2) tma_prefetch_desc(&map_o2);
+    }
     uint32_t lt = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int64_t m = (tile / num_n) * BLOCK_M + 32 * q + lane;
@@ -327,7 +347,62 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
         }
-        if (m < M) {
+        if (tma_out) {
+          // values -> swizzled 32 x 32 tile in shared memory -> one TMA store per warp (clipped at M and N)
+          float4 aa[8];
+          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading this warp's tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = sum[j + e] * rs * s_cs[c0 + j + e] + s_cb[c0 + j + e];
+            const bool in4 = (m < M) && (n + 3 < N);
+            if (rrow) {
+              if (in4) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
+                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+              } else if (m < M) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < N) v[e] += rrow[n + e];
+              }
+            }
+            if (ep.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (ep.act == 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * ep.slope;
+            }
+            *reinterpret_cast<float4*>(stg_ptr + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            if (orow) {
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (in4) a4 = *reinterpret_cast<const float4*>(arow + n);
+              else if (m < M) {
+                if (n < N) a4.x = arow[n];
+                if (n + 1 < N) a4.y = arow[n + 1];
+                if (n + 2 < N) a4.z = arow[n + 2];
+                if (n + 3 < N) a4.w = arow[n + 3];
+              }
+              aa[j >> 2] = make_float4(v[0] + a4.x, v[1] + a4.y, v[2] + a4.z, v[3] + a4.w);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          const int row0 = (int)((tile / num_n) * BLOCK_M) + 32 * q;
+          if (lane == 0) tma_store_2d(&map_c, stg, n0 + c0, row0);
+          if (orow) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(stg_ptr + lane * 128 + ((c ^ (lane & 7)) << 4)) = aa[c];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&map_o2, stg, n0 + c0, row0);
+          }
+        } else if (m < M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int n = n0 + c0 + j;
@@ -372,6 +447,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
       }
       __syncwarp();
     }
+    if (tma_out && lane == 0) tma_store_wait_all();  // every store of this warp has landed before the CTA exits
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -415,6 +491,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats), box = [box_rows, 32 floats], SWIZZLE_128B.
 int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t ld, int box_rows) {
+  if (ptr == nullptr) { memset(map, 0, sizeof(*map)); return KPREG_OK; }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return KPREG_E_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -432,8 +509,8 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t
 }
 
 template <int BLOCK_N, int NUM_HI, int STAGES>
-int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, float* C, int64_t M, int N, int K,
-                       int ldc, const Epilogue& ep, cudaStream_t stream) {
+int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
+                       const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -442,7 +519,7 @@ int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUte
   }
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -494,14 +571,21 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   if (rc) return rc;
   auto aligned = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0); };
   const int vec_ok = aligned(c, ldc) && aligned(residual, ld_res) && aligned(out2, ld2) && aligned(addend, ld_add);
-  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok};
+  // outputs leave through TMA when every pointer / pitch is 16-byte aligned (the store clips at M and N itself)
+  const int tma_store = vec_ok;
+  CUtensorMap mc, mo2;
+  rc = make_map(&mc, tma_store ? c : nullptr, m, n, ldc, 32);
+  if (rc) return rc;
+  rc = make_map(&mo2, (tma_store && out2) ? out2 : nullptr, m, n, ld2, 32);
+  if (rc) return rc;
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, tma_store};
   if (num_hi == 3) {
-    if (block_n == 32) return launch_tile_config<32, 3, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
-    return launch_tile_config<64, 3, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 32) return launch_tile_config<32, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<64, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
   }
-  if (block_n == 32) return launch_tile_config<32, 1, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
-  if (block_n == 64) return launch_tile_config<64, 1, 4>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
-  return launch_tile_config<128, 1, 3>(ma, mbh, mbl, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 32) return launch_tile_config<32, 1, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 1, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 1, 3>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
 }
 
 }  // namespace kpreg

@@ -13,16 +13,17 @@ import torch
 import torch.nn as nn
 
 
-def _folded_bn(bn: nn.BatchNorm1d):
-    """Eval-mode BatchNorm1d as a per-channel (scale, shift), cached until a parameter or statistic changes."""
-    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+def _folded(linear: nn.Linear, bn: nn.BatchNorm1d):
+    """(weight', shift) with the eval-mode BatchNorm1d folded into the bias-free Linear that precedes it:
+    bn(x W^T) = x (diag(s) W)^T + (beta - mean * s),  s = gamma / sqrt(var + eps).
+    Cached on the BatchNorm module until a parameter or running statistic changes."""
+    key = (linear.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, linear.weight.data_ptr(), bn.running_mean.data_ptr())
     cache = getattr(bn, "_kpreg_folded", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
             scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-            shift = bn.bias - bn.running_mean * scale
-        cache = (key, scale.contiguous(), shift.contiguous())
+            cache = (key, (linear.weight * scale[:, None]).contiguous(), (bn.bias - bn.running_mean * scale).contiguous())
         bn._kpreg_folded = cache
     return cache[1], cache[2]
 
@@ -52,31 +53,44 @@ class my_Bottle2neck(nn.Module):
         self.width = width
 
     def _fused_forward(self, x):
-        """Inference on CUDA: every Linear + eval-BatchNorm + ReLU is one tensor-core GEMM with a fused
-        epilogue; the chain's `previous output + next group` sums are emitted by the producing GEMM."""
+        """Inference on CUDA: every Linear + eval-BatchNorm (+ ReLU) is one tensor-core GEMM with a fused
+        epilogue; each chained layer also emits `its output + the next group` (the next layer's input); the
+        residual projection is folded into the last GEMM by concatenating its input and weights along K."""
         from . import kpconv_blocks as kb
         from . import ops
-        w, s = self.width, self.scale
+        w, n_groups = self.width, self.scale
         gemm = kb.DEFAULT_GEMM
-        sc, sh = _folded_bn(self.bn1)
-        t = ops.linear_forward(x, self.conv1.weight, sc, sh, act="relu", gemm=gemm)          # [N, w*s]
-        cat = torch.empty_like(t)
+        wt, sh = _folded(self.conv1, self.bn1)
+        t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm)                      # [N, w * scale]
+        fuse_res = self.downsample is not None and x.shape[1] % 4 == 0
+        k_cat = w * n_groups
+        z = torch.empty((t.shape[0], k_cat + (x.shape[1] if fuse_res else 0)), dtype=t.dtype, device=t.device)
         scratch = [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
         inp = t[:, :w]
         for i in range(self.nums):
-            sc, sh = _folded_bn(self.bns[i])
+            wt, sh = _folded(self.convs[i], self.bns[i])
             nxt = i + 1 < self.nums
-            ops.linear_forward(inp, self.convs[i].weight, sc, sh, act="relu", out=cat[:, i * w:(i + 1) * w],
+            ops.linear_forward(inp, wt, None, sh, act="relu", out=z[:, i * w:(i + 1) * w],
                                out2=scratch[i & 1] if nxt else None, addend=t[:, (i + 1) * w:(i + 2) * w] if nxt else None,
                                gemm=gemm)
             inp = scratch[i & 1]
-        cat[:, self.nums * w:] = t[:, self.nums * w:]
+        z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
+        w3, b3 = _folded(self.conv3, self.bn3)
+        if fuse_res:
+            # relu(bn3(cat W3^T) + bn_d(x Wd^T)) = relu([cat | x] [W3' | Wd']^T + b3' + bd')
+            z[:, k_cat:] = x
+            wd, bd = _folded(self.downsample[0], self.downsample[1])
+            key = (self.bn3._kpreg_folded[0], self.downsample[1]._kpreg_folded[0])
+            cache = getattr(self, "_kpreg_joint", None)
+            if cache is None or cache[0] != key:
+                cache = (key, torch.cat([w3, wd], 1).contiguous(), (b3 + bd).contiguous())
+                self._kpreg_joint = cache
+            return ops.linear_forward(z, cache[1], None, cache[2], act="relu", gemm=gemm)
         residual = x
         if self.downsample is not None:
-            sc, sh = _folded_bn(self.downsample[1])
-            residual = ops.linear_forward(x, self.downsample[0].weight, sc, sh, gemm=gemm)
-        sc, sh = _folded_bn(self.bn3)
-        return ops.linear_forward(cat, self.conv3.weight, sc, sh, residual=residual, act="relu", gemm=gemm)
+            wd, bd = _folded(self.downsample[0], self.downsample[1])
+            residual = ops.linear_forward(x, wd, None, bd, gemm=gemm)
+        return ops.linear_forward(z[:, :k_cat], w3, None, b3, residual=residual, act="relu", gemm=gemm)
 
     def forward(self, x):
         if (not self.training and x.is_cuda and not torch.is_grad_enabled() and self.stype == 'normal'
