@@ -322,12 +322,13 @@ def _res2net(x, sd, prefix, training=False):
     return F.relu(out + res)
 
 
-def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool = False):
+def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool = False, keep_grad: bool = False):
     """KPFEncoder.forward (models/backbone_kpconv/finegrained_kpconv.py:86-95) over SimpleBlock /
     ResnetBottleneckBlock (finegrained_kpconv_blocks.py:578-634, 637-727), driven by a state_dict
     with the reference's parameter names (``encoder_blocks.{i}.KPConv.weights`` ...).
     Returns (features, skip_x)."""
-    sd = {k: v.detach().cpu().float() for k, v in sd.items()}
+    if not keep_grad:
+        sd = {k: v.detach().cpu().float() for k, v in sd.items()}
     x = torch.as_tensor(x).float().cpu()
     pts = [torch.as_tensor(p).float().cpu() for p in batch["points"]]
     lens = [np.asarray(torch.as_tensor(l).cpu()) for l in batch["stack_lengths"]]

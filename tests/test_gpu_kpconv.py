@@ -139,3 +139,44 @@ def test_encoder_3dmatch_full_size_vs_oracle(oracle):
         got, _ = enc(x0.cuda(), meta)
     assert got.shape[1] == 1024
     assert rel_err(got.cpu().numpy(), want.numpy()) < 5 * TOL  # 11 blocks deep
+
+
+def test_training_step_3dmatch_shape_vs_oracle_autograd(oracle):
+    """BASELINE config 4 in small: forward + backward through all 11 KPConv ops (and the 3 max_pools) of the
+    3DMatch encoder, loss = sum(output); weight gradients vs the CPU oracle's autograd (1e-3 relative: the
+    oracle itself runs fp32 with a different summation order through 11 blocks)."""
+    cfg = kpconv_config("3dmatch")
+    torch.manual_seed(2)
+    np.random.seed(2)
+    enc = KPFEncoder(cfg, cfg.d_embed).train()
+    src, tgt, _ = synthetic.threedmatch_pair(seed=41, n_raw=6000)
+    meta = Preprocessor(cfg)([cuda(src), cuda(tgt)])
+    x0 = torch.ones((meta["points"][0].shape[0], 1))
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    watch = ["encoder_blocks.0.KPConv.weights", "encoder_blocks.5.KPConv.weights", "encoder_blocks.10.KPConv.weights"]
+    for k in watch:
+        sd[k].requires_grad_(True)
+    with torch.enable_grad():
+        want, _ = oracle.encoder_forward(sd, cfg, x0, {k: [t.cpu() for t in v] for k, v in meta.items()}, training=True,
+                                         keep_grad=True)
+        want.sum().backward()
+    enc = enc.cuda()
+    got, _ = enc(x0.cuda(), meta)
+    got.sum().backward()
+    assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-3
+    params = dict(enc.named_parameters())
+    for k in watch:
+        g = params[k.replace("encoder_blocks.", "encoder_blocks.")].grad
+        assert rel_err(g.cpu().numpy(), sd[k].grad.numpy()) < 2e-3, k
+
+
+def test_pyramid_and_encoder_mcd_full_size(oracle):
+    """BASELINE config 3 shape: 2 x 120 k LiDAR-like points (sparse grid, variable row widths)."""
+    cfg = kpconv_config("mcd")
+    src, tgt, _ = synthetic.mcd_pair(seed=2)
+    meta = Preprocessor(cfg, index_dtype=torch.int32)([cuda(src), cuda(tgt)])
+    want = oracle.preprocess([src, tgt], cfg, impl="ref" if oracle.have_ref() else "port")
+    from gpu_util import check_pyramid, meta_to_numpy
+    check_pyramid(oracle, meta_to_numpy(meta), want, cfg)
+    widths = [int(t.shape[1]) for t in meta["neighbors"]]
+    assert widths[0] < 40  # sparse LiDAR: the first levels do not saturate the neighbourhood limit
