@@ -15,6 +15,8 @@
 //                     fp32 CUDA-core GEMM below (also used by the backward pass).
 // Shadow neighbours (index >= n_s; the reference's 1e6 point and zero feature row, :296/:375)
 // contribute exactly zero and are skipped.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kpreg {
@@ -32,6 +34,7 @@ namespace {
 constexpr int KMAX = 16;             // kernel points handled per neighbour (reference ships 15)
 constexpr int KSTRIDE = 20;          // floats per neighbour row of influences in shared memory: 16-byte aligned, conflict-free float4 stores
 constexpr int kGatherWarps = 4;      // warps (= queries in flight) per CTA
+bool g_gather_mma = true;            // aggregate on mma.sync (3xTF32); false = fp32 FFMA kernel (KPREG_GATHER_FFMA=1)
 
 __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ x, int64_t n_s, int c_in,
                                                       unsigned char* __restrict__ pos) {
@@ -139,6 +142,144 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
           const int c = lane + 32 * cc;
           if (c < c_in) arow[k * c_in + c] = acc[cc][k];
         }
+      }
+    }
+    if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+  }
+}
+
+// ---- tensor-core variant of the gather/aggregate step ---------------------------------------------------
+// agg[n, k, c] = sum_h infl[n,h,k] * x[idx[n,h], c] is, per query, a [16 x H] x [H x c_in] product.  One warp per
+// query runs it on mma.sync m16n8k8 (TF32, fp32 accumulate) with the same 3xTF32 operand split as the
+// contraction GEMM (fp32-grade accuracy): M = kernel points (15 + 1 zero row), K = 8 neighbours per step,
+// N = 8 channels per tile.  Every lane computes exactly the four influences of its A fragment
+// (kernel points g, g+8 x neighbours t, t+4 with g = lane/4, t = lane%4) — no influence is computed twice —
+// and loads its B fragment straight from the two neighbours' feature rows (8 lanes read 32 contiguous bytes).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__device__ __forceinline__ float influence_one(float rx, float ry, float rz, float kx, float ky, float kz, float inv_extent,
+                                               float extent, int influence, float& d2_out) {
+  const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
+  const float d2 = dx * dx + dy * dy + dz * dz;
+  d2_out = d2;
+  if (influence == 1) return fmaxf(1.0f - d2 * rsqrtf(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
+  if (influence == 2) { const float sig = extent * 0.3f; return expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
+  return 1.0f;
+}
+
+template <typename IdxT, int NT>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
+__global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
+    const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
+    const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
+    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float inv_extent = 1.0f / extent;
+  // this lane's two kernel points (rows g and g + 8 of the A fragment); row 15 is the zero pad when K = 15
+  const bool k0_ok = g < n_kpts, k1_ok = g + 8 < n_kpts;
+  const float k0x = k0_ok ? kernel_points[3 * g] : 0.f, k0y = k0_ok ? kernel_points[3 * g + 1] : 0.f,
+              k0z = k0_ok ? kernel_points[3 * g + 2] : 0.f;
+  const float k1x = k1_ok ? kernel_points[3 * (g + 8)] : 0.f, k1y = k1_ok ? kernel_points[3 * (g + 8) + 1] : 0.f,
+              k1z = k1_ok ? kernel_points[3 * (g + 8) + 2] : 0.f;
+
+  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+    const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
+    // neighbours h = lane and h = lane + 32: index and relative position, fetched once, shuffled per k-step
+    int64_t jn[2];
+    float rx[2], ry[2], rz[2];
+    int num = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int h = lane + 32 * r;
+      int64_t j = n_s;
+      if (h < n_nbrs) j = (int64_t)idx[n * n_nbrs + h];
+      const bool valid = j >= 0 && j < n_s;
+      jn[r] = valid ? j : -1;
+      rx[r] = ry[r] = rz[r] = 0.f;
+      if (valid) { rx[r] = s_pts[3 * j] - qx; ry[r] = s_pts[3 * j + 1] - qy; rz[r] = s_pts[3 * j + 2] - qz; }
+      num += __popc(__ballot_sync(0xffffffffu, valid && row_pos[j] != 0));
+    }
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+    for (int h0 = 0; h0 < n_nbrs; h0 += 8) {
+      // neighbours of this lane's fragment columns: h0 + t and h0 + t + 4
+      const int ha = h0 + t, hb = h0 + t + 4;
+      const int ra = ha >> 5, rb = hb >> 5;  // warp-uniform per k-step (h0 is a multiple of 8)
+      const int64_t ja = __shfl_sync(0xffffffffu, ra ? jn[1] : jn[0], ha & 31);
+      const int64_t jb = __shfl_sync(0xffffffffu, rb ? jn[1] : jn[0], hb & 31);
+      const float ax = __shfl_sync(0xffffffffu, ra ? rx[1] : rx[0], ha & 31), ay = __shfl_sync(0xffffffffu, ra ? ry[1] : ry[0], ha & 31),
+                  az = __shfl_sync(0xffffffffu, ra ? rz[1] : rz[0], ha & 31);
+      const float bx = __shfl_sync(0xffffffffu, rb ? rx[1] : rx[0], hb & 31), by = __shfl_sync(0xffffffffu, rb ? ry[1] : ry[0], hb & 31),
+                  bz = __shfl_sync(0xffffffffu, rb ? rz[1] : rz[0], hb & 31);
+      const bool va = ja >= 0, vb = jb >= 0;
+      if (!__any_sync(0xffffffffu, va || vb)) continue;  // eight shadow neighbours: nothing to add
+      float w[4], d2[4];
+      w[0] = influence_one(ax, ay, az, k0x, k0y, k0z, inv_extent, extent, influence, d2[0]);  // (k = g,     h = t)
+      w[1] = influence_one(ax, ay, az, k1x, k1y, k1z, inv_extent, extent, influence, d2[1]);  // (k = g + 8, h = t)
+      w[2] = influence_one(bx, by, bz, k0x, k0y, k0z, inv_extent, extent, influence, d2[2]);  // (k = g,     h = t + 4)
+      w[3] = influence_one(bx, by, bz, k1x, k1y, k1z, inv_extent, extent, influence, d2[3]);  // (k = g + 8, h = t + 4)
+      if (!k0_ok) { w[0] = w[2] = 0.f; d2[0] = d2[2] = 3.4e38f; }
+      if (!k1_ok) { w[1] = w[3] = 0.f; d2[1] = d2[3] = 3.4e38f; }
+      if (!va) w[0] = w[1] = 0.f;
+      if (!vb) w[2] = w[3] = 0.f;
+      if (aggregation == 1) {
+        // 'closest': only the nearest kernel point of each neighbour keeps its influence (first minimum wins)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float best = d2[2 * hh];
+          int best_k = g;
+          if (d2[2 * hh + 1] < best) { best = d2[2 * hh + 1]; best_k = g + 8; }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {  // reduce over the eight lanes that share this neighbour (same t)
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+            if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+          }
+          if (best_k != g) w[2 * hh] = 0.f;
+          if (best_k != g + 8) w[2 * hh + 1] = 0.f;
+        }
+      }
+      float a_hi[4], a_lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a_hi[i] = tf32_rn(w[i]); a_lo[i] = tf32_rn(w[i] - a_hi[i]); }
+      const float* __restrict__ xa = x + (va ? ja : 0) * c_in;
+      const float* __restrict__ xb = x + (vb ? jb : 0) * c_in;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int c = 8 * i + g;
+        const float b0 = (va && c < c_in) ? xa[c] : 0.f;
+        const float b1 = (vb && c < c_in) ? xb[c] : 0.f;
+        const float b0h = tf32_rn(b0), b1h = tf32_rn(b1);
+        const float b0l = tf32_rn(b0 - b0h), b1l = tf32_rn(b1 - b1h);
+        mma_tf32(acc[i], a_lo, b0h, b1h);
+        mma_tf32(acc[i], a_hi, b0l, b1l);
+        mma_tf32(acc[i], a_hi, b0h, b1h);
+      }
+    }
+    // D fragment: rows (kernel points) g and g + 8, columns (channels) 8 i + 2 t, + 1
+    float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int c = 8 * i + 2 * t;
+      if (k0_ok) {
+        if (c < c_in) arow[g * c_in + c] = acc[i][0];
+        if (c + 1 < c_in) arow[g * c_in + c + 1] = acc[i][1];
+      }
+      if (k1_ok) {
+        if (c < c_in) arow[(g + 8) * c_in + c] = acc[i][2];
+        if (c + 1 < c_in) arow[(g + 8) * c_in + c + 1] = acc[i][3];
       }
     }
     if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
@@ -336,6 +477,21 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   if (blocks > cap) blocks = cap;
   const IdxT* ip = static_cast<const IdxT*>(idx);
   ProfScope prof(KPREG_FAM_GATHER, stream);
+  if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && g_gather_mma) {
+#define KP_GATHER_MMA(NT)                                                                                                       \
+  k_kpconv_gather_mma<IdxT, NT><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs,   \
+                                                                          n_kpts, c_in, extent, influence, aggregation, agg,    \
+                                                                          inv_num)
+    if (c_in <= 8) KP_GATHER_MMA(1);
+    else if (c_in <= 16) KP_GATHER_MMA(2);
+    else if (c_in <= 32) KP_GATHER_MMA(4);
+    else if (c_in <= 64) KP_GATHER_MMA(8);
+    else if (c_in <= 128) KP_GATHER_MMA(16);
+    else KP_GATHER_MMA(32);
+#undef KP_GATHER_MMA
+    KP_LAUNCH_CHECK();
+    return KPREG_OK;
+  }
 #define KP_GATHER(CPL)                                                                                                     \
   k_kpconv_gather<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, \
                                                                        n_kpts, c_in, extent, influence, aggregation, agg,  \
@@ -382,6 +538,15 @@ int check_kpconv_args(int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in
 }  // namespace kpreg
 
 using namespace kpreg;
+
+namespace {
+struct GatherModeInit {
+  GatherModeInit() {
+    const char* e = getenv("KPREG_GATHER_FFMA");
+    if (e && e[0] == '1') kpreg::g_gather_mma = false;
+  }
+} g_gather_mode_init;
+}  // namespace
 
 extern "C" int kpreg_kpconv_workspace_bytes(int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out, int backward,
                                             size_t* bytes) {

@@ -322,15 +322,16 @@ def _res2net(x, sd, prefix, training=False):
     return F.relu(out + res)
 
 
-def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool = False, keep_grad: bool = False):
+def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool = False, keep_grad: bool = False,
+                    dtype=torch.float32):
     """KPFEncoder.forward (models/backbone_kpconv/finegrained_kpconv.py:86-95) over SimpleBlock /
     ResnetBottleneckBlock (finegrained_kpconv_blocks.py:578-634, 637-727), driven by a state_dict
     with the reference's parameter names (``encoder_blocks.{i}.KPConv.weights`` ...).
     Returns (features, skip_x)."""
     if not keep_grad:
-        sd = {k: v.detach().cpu().float() for k, v in sd.items()}
-    x = torch.as_tensor(x).float().cpu()
-    pts = [torch.as_tensor(p).float().cpu() for p in batch["points"]]
+        sd = {k: (v.detach().cpu().to(dtype) if v.is_floating_point() else v.detach().cpu()) for k, v in sd.items()}
+    x = torch.as_tensor(x).to(dtype).cpu()
+    pts = [torch.as_tensor(p).to(dtype).cpu() for p in batch["points"]]
     lens = [np.asarray(torch.as_tensor(l).cpu()) for l in batch["stack_lengths"]]
     r = cfg.first_subsampling_dl * cfg.conv_radius
     layer, skips = 0, []
@@ -349,7 +350,7 @@ def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool =
             qp, sp, idx, post = pts[layer + 1], pts[layer], batch["pools"][layer], lens[layer + 1]
         else:
             qp, sp, idx, post = pts[layer], pts[layer], batch["neighbors"][layer], lens[layer]
-        kw = dict(KP_extent=extent, KP_influence=cfg.KP_influence, aggregation_mode=cfg.aggregation_mode)
+        kw = dict(KP_extent=extent, KP_influence=cfg.KP_influence, aggregation_mode=cfg.aggregation_mode, dtype=dtype)
         if name.startswith("simple"):
             y = kpconv_forward(qp, sp, idx, x, sd[pre + ".KPConv.weights"], sd[pre + ".KPConv.kernel_points"], **kw)
             x = F.leaky_relu(_instance_norm(y, post), 0.1)

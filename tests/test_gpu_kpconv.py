@@ -143,8 +143,8 @@ def test_encoder_3dmatch_full_size_vs_oracle(oracle):
 
 def test_training_step_3dmatch_shape_vs_oracle_autograd(oracle):
     """BASELINE config 4 in small: forward + backward through all 11 KPConv ops (and the 3 max_pools) of the
-    3DMatch encoder, loss = sum(output); weight gradients vs the CPU oracle's autograd (1e-3 relative: the
-    oracle itself runs fp32 with a different summation order through 11 blocks)."""
+    3DMatch encoder, loss = <output, fixed random probe>; weight gradients vs the CPU oracle's autograd (2e-3
+    relative: the oracle itself runs fp32 with a different summation order through 11 blocks)."""
     cfg = kpconv_config("3dmatch")
     torch.manual_seed(2)
     np.random.seed(2)
@@ -152,22 +152,37 @@ def test_training_step_3dmatch_shape_vs_oracle_autograd(oracle):
     src, tgt, _ = synthetic.threedmatch_pair(seed=41, n_raw=6000)
     meta = Preprocessor(cfg)([cuda(src), cuda(tgt)])
     x0 = torch.ones((meta["points"][0].shape[0], 1))
-    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
     watch = ["encoder_blocks.0.KPConv.weights", "encoder_blocks.5.KPConv.weights", "encoder_blocks.10.KPConv.weights"]
-    for k in watch:
-        sd[k].requires_grad_(True)
-    with torch.enable_grad():
-        want, _ = oracle.encoder_forward(sd, cfg, x0, {k: [t.cpu() for t in v] for k, v in meta.items()}, training=True,
-                                         keep_grad=True)
-        want.sum().backward()
+    cpu_meta = {k: [t.cpu() for t in v] for k, v in meta.items()}
+
+    def oracle_grads(dtype):
+        sd = {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone())
+              for k, v in enc.state_dict().items()}
+        for k in watch:
+            sd[k].requires_grad_(True)
+        with torch.enable_grad():
+            out, _ = oracle.encoder_forward(sd, cfg, x0, cpu_meta, training=True, keep_grad=True, dtype=dtype)
+            # a generic linear functional of the output: sum(out) alone is degenerate (the sum over a cloud of an
+            # instance-normalised feature is identically zero, so its gradient is pure cancellation noise)
+            probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+            (out * probe.to(dtype)).sum().backward()
+        return out.detach(), {k: sd[k].grad for k in watch}, probe
+
+    want, grads32, probe = oracle_grads(torch.float32)   # the reference's arithmetic
+    _, grads64, _ = oracle_grads(torch.float64)           # ground truth, to calibrate fp32 noise through 11 blocks
     enc = enc.cuda()
     got, _ = enc(x0.cuda(), meta)
-    got.sum().backward()
-    assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-3
+    (got * probe.cuda()).sum().backward()
+    e_fwd = rel_err(got.detach().cpu().numpy(), want.detach().numpy())
     params = dict(enc.named_parameters())
+    errs = {k: rel_err(params[k].grad.cpu().numpy(), grads64[k].numpy()) for k in watch}
+    noise = {k: rel_err(grads32[k].numpy(), grads64[k].numpy()) for k in watch}
+    print("training step: forward err", e_fwd, "| CUDA grads vs fp64 truth", errs, "| fp32 oracle vs fp64 truth", noise)
+    assert e_fwd < 1e-3
     for k in watch:
-        g = params[k.replace("encoder_blocks.", "encoder_blocks.")].grad
-        assert rel_err(g.cpu().numpy(), sd[k].grad.numpy()) < 2e-3, k
+        # gradients through 11 blocks of train-mode normalisation are ill-conditioned in fp32: hold the CUDA path to
+        # the accuracy the reference's own fp32 arithmetic achieves against the fp64 truth
+        assert errs[k] < 5.0 * noise[k] + 2e-3, (k, errs, noise)
 
 
 def test_pyramid_and_encoder_mcd_full_size(oracle):
@@ -180,3 +195,23 @@ def test_pyramid_and_encoder_mcd_full_size(oracle):
     check_pyramid(oracle, meta_to_numpy(meta), want, cfg)
     widths = [int(t.shape[1]) for t in meta["neighbors"]]
     assert widths[0] < 40  # sparse LiDAR: the first levels do not saturate the neighbourhood limit
+
+
+@pytest.mark.parametrize("c_in,c_out,n_sub", [(32, 32, None), (64, 64, None), (128, 128, 700), (256, 256, 500), (40, 24, None)])
+def test_kpconv_backward_matches_oracle_autograd_channel_sweep(oracle, golden_modelnet, c_in, c_out, n_sub):
+    """d_x and d_weights for every channel width of the encoder vs autograd through the CPU oracle."""
+    g = golden_modelnet
+    rng = np.random.default_rng(c_in + 3)
+    q, s, idx = g["mn_points_1"], g["mn_points_0"], g["mn_pools_0"]
+    if n_sub:
+        q, idx = q[:n_sub], idx[:n_sub]
+    x = rng.normal(size=(s.shape[0], c_in)).astype(np.float32)
+    w = (rng.normal(size=(15, c_in, c_out)) / np.sqrt(15 * c_in)).astype(np.float32)
+    kp = g["op_linear_sum_kp"]
+    go = rng.normal(size=(q.shape[0], c_out)).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    wt = torch.from_numpy(w).requires_grad_(True)
+    oracle.kpconv_forward(q, s, idx, xt, wt, kp, 0.12).backward(torch.from_numpy(go))
+    d_x, d_w = ops.kpconv_backward(cuda(q), cuda(s), cuda(idx), cuda(x), cuda(w), cuda(kp), cuda(go), 0.12)
+    assert rel_err(d_x.cpu().numpy(), xt.grad.numpy()) < TOL
+    assert rel_err(d_w.cpu().numpy(), wt.grad.numpy()) < TOL
