@@ -30,19 +30,19 @@ _SIGNATURES = {
     "kpreg_subsample_batch": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_int, _c_ptr, _c_ptr,
                                        _c_ptr, _c_size, _c_ptr]),
     "kpreg_grid_workspace_bytes": (_c_int, [_c_i64, _c_int, ctypes.POINTER(_c_size)]),
-    "kpreg_grid_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_grid_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_ptr, _c_size, _c_ptr, _c_ptr]),
     "kpreg_grid_query": (_c_int, [_c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_i64, _c_f32, _c_int, _c_int,
-                                  _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+                                  _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     "kpreg_pack_rows": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_ptr]),
     "kpreg_kpconv_workspace_bytes": (_c_int, [_c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                               ctypes.POINTER(_c_size)]),
     "kpreg_kpconv_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
-                                      _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_int, _c_ptr,
+                                      _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_int, _c_ptr, _c_ptr,
                                       _c_ptr, _c_size, _c_ptr]),
     "kpreg_kpconv_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64,
-                                       _c_i64, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_ptr,
+                                       _c_i64, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_ptr, _c_ptr,
                                        _c_ptr, _c_ptr, _c_size, _c_ptr]),
-    "kpreg_max_pool_forward": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr,
+    "kpreg_max_pool_forward": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
                                         _c_ptr]),
     "kpreg_max_pool_backward": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_int, _c_ptr, _c_ptr]),
     "kpreg_linear_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),

@@ -51,62 +51,75 @@ __global__ void __launch_bounds__(256) k_linear_simple(const float* __restrict__
   }
 }
 
-constexpr int kStatRows = 128;  // rows per CTA
-constexpr int kStatCh = 64;     // channels per CTA (threadIdx.x & 63), 4 row groups
+constexpr int kStatRows = 256;  // rows per CTA
+constexpr int kStatCh = 64;     // channels per CTA: 16 threads x float4; 16 row groups
 
-// stats[(cloud * C + ch) * 2 + {0,1}] += {sum x, sum x^2} in fp64
+__device__ __forceinline__ void stat_flush(double* __restrict__ stats, int cloud, int channels, int ch, const double (&sum)[4],
+                                           const double (&sq)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    double* dst = stats + ((int64_t)cloud * channels + ch + e) * 2;
+    atomicAdd(dst, sum[e]);
+    atomicAdd(dst + 1, sq[e]);
+  }
+}
+
+// stats[(cloud * C + ch) * 2 + {0,1}] += {sum x, sum x^2} in fp64.  Each thread streams float4 (4 channels) of 16
+// rows; a CTA covers 256 rows x 64 channels and issues one atomic pair per channel when it lies inside one cloud.
 __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
                                                        int n_clouds, int64_t n_rows, int channels, double* __restrict__ stats) {
-  __shared__ double s_sum[4][kStatCh], s_sq[4][kStatCh];
-  const int cx = threadIdx.x & (kStatCh - 1), ry = threadIdx.x >> 6;
-  const int ch = blockIdx.y * kStatCh + cx;
+  __shared__ double s_sum[16][kStatCh], s_sq[16][kStatCh];
+  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int ch = blockIdx.y * kStatCh + cx * 4;
   const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
   const int64_t r1 = min(n_rows, r0 + kStatRows);
   const int c_first = cloud_of(off, n_clouds, r0);
   const int c_last = cloud_of(off, n_clouds, r1 - 1);
-  const bool live = ch < channels;
+  const bool live = ch < channels;  // channels is a multiple of 4
+  double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
   if (c_first == c_last) {
-    double sum = 0.0, sq = 0.0;
-    if (live)
-      for (int64_t r = r0 + ry; r < r1; r += 4) {
-        const double v = (double)x[r * ldx + ch];
-        sum += v;
-        sq += v * v;
+    if (live) {
+#pragma unroll 4
+      for (int64_t r = r0 + ry; r < r1; r += 16) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+        sum[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
+        sum[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
+        sum[2] += (double)v.z; sq[2] += (double)v.z * (double)v.z;
+        sum[3] += (double)v.w; sq[3] += (double)v.w * (double)v.w;
       }
-    s_sum[ry][cx] = sum;
-    s_sq[ry][cx] = sq;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s_sum[ry][cx * 4 + e] = sum[e]; s_sq[ry][cx * 4 + e] = sq[e]; }
     __syncthreads();
-    if (ry == 0 && live) {
-      sum = s_sum[0][cx] + s_sum[1][cx] + s_sum[2][cx] + s_sum[3][cx];
-      sq = s_sq[0][cx] + s_sq[1][cx] + s_sq[2][cx] + s_sq[3][cx];
-      double* dst = stats + ((int64_t)c_first * channels + ch) * 2;
-      atomicAdd(dst, sum);
-      atomicAdd(dst + 1, sq);
+    if (threadIdx.x < kStatCh) {
+      const int c = blockIdx.y * kStatCh + threadIdx.x;
+      if (c < channels) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) { a += s_sum[g][threadIdx.x]; b += s_sq[g][threadIdx.x]; }
+        double* dst = stats + ((int64_t)c_first * channels + c) * 2;
+        atomicAdd(dst, a);
+        atomicAdd(dst + 1, b);
+      }
     }
   } else if (live) {
     // chunk straddles a cloud boundary: flush per thread whenever the cloud changes
     int c = -1;
-    double sum = 0.0, sq = 0.0;
-    for (int64_t r = r0 + ry; r < r1; r += 4) {
+    for (int64_t r = r0 + ry; r < r1; r += 16) {
       const int cr = cloud_of(off, n_clouds, r);
       if (cr != c) {
-        if (c >= 0) {
-          double* dst = stats + ((int64_t)c * channels + ch) * 2;
-          atomicAdd(dst, sum);
-          atomicAdd(dst + 1, sq);
-        }
+        if (c >= 0) stat_flush(stats, c, channels, ch, sum, sq);
         c = cr;
-        sum = sq = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sum[e] = sq[e] = 0.0;
       }
-      const double v = (double)x[r * ldx + ch];
-      sum += v;
-      sq += v * v;
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+      sum[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
+      sum[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
+      sum[2] += (double)v.z; sq[2] += (double)v.z * (double)v.z;
+      sum[3] += (double)v.w; sq[3] += (double)v.w * (double)v.w;
     }
-    if (c >= 0) {
-      double* dst = stats + ((int64_t)c * channels + ch) * 2;
-      atomicAdd(dst, sum);
-      atomicAdd(dst + 1, sq);
-    }
+    if (c >= 0) stat_flush(stats, c, channels, ch, sum, sq);
   }
 }
 

@@ -76,14 +76,16 @@ template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
-    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num) {
+    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num,
+    const int32_t* __restrict__ order) {
   __shared__ float s_kp[KMAX * 3];
   __shared__ __align__(16) float s_w[kGatherWarps][32][KSTRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
 
-  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     float acc[CPL][KMAX];
 #pragma unroll
@@ -181,7 +183,8 @@ template <typename IdxT, int NT>  // NT = number of 8-channel tiles (c_in <= 8 *
 __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
-    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num) {
+    int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num,
+    const int32_t* __restrict__ order) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const float inv_extent = 1.0f / extent;
@@ -192,7 +195,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
   const float k1x = k1_ok ? kernel_points[3 * (g + 8)] : 0.f, k1y = k1_ok ? kernel_points[3 * (g + 8) + 1] : 0.f,
               k1z = k1_ok ? kernel_points[3 * (g + 8) + 2] : 0.f;
 
-  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     // neighbours h = lane and h = lane + 32: index and relative position, fetched once, shuffled per k-step
     int64_t jn[2];
@@ -291,13 +295,14 @@ template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx,
     const float* __restrict__ kernel_points, const float* __restrict__ d_agg, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
-    int c_in, float extent, int influence, int aggregation, float* __restrict__ d_x) {
+    int c_in, float extent, int influence, int aggregation, float* __restrict__ d_x, const int32_t* __restrict__ order) {
   __shared__ float s_kp[KMAX * 3];
   __shared__ __align__(16) float s_w[kGatherWarps][32][KSTRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
-  for (int64_t n = (int64_t)blockIdx.x * kGatherWarps + warp; n < n_q; n += (int64_t)gridDim.x * kGatherWarps) {
+  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     float da[CPL][KMAX];
     const float* __restrict__ drow = d_agg + n * (int64_t)n_kpts * c_in;
@@ -471,7 +476,7 @@ KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in
 template <typename IdxT>
 int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const float* x, const unsigned char* row_pos,
                   const float* kp, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence,
-                  int aggregation, float* agg, float* inv_num, cudaStream_t stream) {
+                  int aggregation, float* agg, float* inv_num, const int32_t* order, cudaStream_t stream) {
   int blocks = ceil_div(n_q, kGatherWarps);
   const int cap = kNumSMs * 32;
   if (blocks > cap) blocks = cap;
@@ -481,7 +486,7 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
 #define KP_GATHER_MMA(NT)                                                                                                       \
   k_kpconv_gather_mma<IdxT, NT><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs,   \
                                                                           n_kpts, c_in, extent, influence, aggregation, agg,    \
-                                                                          inv_num)
+                                                                          inv_num, order)
     if (c_in <= 8) KP_GATHER_MMA(1);
     else if (c_in <= 16) KP_GATHER_MMA(2);
     else if (c_in <= 32) KP_GATHER_MMA(4);
@@ -495,7 +500,7 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
 #define KP_GATHER(CPL)                                                                                                     \
   k_kpconv_gather<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, \
                                                                        n_kpts, c_in, extent, influence, aggregation, agg,  \
-                                                                       inv_num)
+                                                                       inv_num, order)
   if (c_in <= 32) KP_GATHER(1);
   else if (c_in <= 64) KP_GATHER(2);
   else if (c_in <= 128) KP_GATHER(4);
@@ -509,14 +514,14 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
 template <typename IdxT>
 int launch_scatter(const float* q_pts, const float* s_pts, const void* idx, const float* kp, const float* d_agg, int64_t n_q,
                    int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence, int aggregation, float* d_x,
-                   cudaStream_t stream) {
+                   const int32_t* order, cudaStream_t stream) {
   int blocks = ceil_div(n_q, kGatherWarps);
   const int cap = kNumSMs * 32;
   if (blocks > cap) blocks = cap;
   const IdxT* ip = static_cast<const IdxT*>(idx);
 #define KP_SCATTER(CPL)                                                                                                  \
   k_kpconv_scatter<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, kp, d_agg, n_q, n_s, n_nbrs,   \
-                                                                        n_kpts, c_in, extent, influence, aggregation, d_x)
+                                                                        n_kpts, c_in, extent, influence, aggregation, d_x, order)
   if (c_in <= 32) KP_SCATTER(1);
   else if (c_in <= 64) KP_SCATTER(2);
   else if (c_in <= 128) KP_SCATTER(4);
@@ -558,7 +563,7 @@ extern "C" int kpreg_kpconv_workspace_bytes(int64_t n_q, int64_t n_s, int n_kpts
 extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, const void* idx, int idx64, const float* x,
                                     const float* weights, const float* kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
                                     int n_kpts, int c_in, int c_out, float kp_extent, int influence, int aggregation, int gemm,
-                                    float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+                                    const int32_t* order, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
   int rc = check_kpconv_args(n_q, n_s, n_nbrs, n_kpts, c_in, c_out, kp_extent, influence, aggregation);
   if (rc) return rc;
   if (n_q == 0) return KPREG_OK;
@@ -573,9 +578,9 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
     KP_LAUNCH_CHECK();
   }
   rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                      influence, aggregation, w.agg, w.inv_num, stream)
+                                      influence, aggregation, w.agg, w.inv_num, order, stream)
              : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                      influence, aggregation, w.agg, w.inv_num, stream);
+                                      influence, aggregation, w.agg, w.inv_num, order, stream);
   if (rc) return rc;
   const int kd = n_kpts * c_in;
   ProfScope prof(KPREG_FAM_CONTRACT, stream);
@@ -591,8 +596,8 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
 extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, const void* idx, int idx64, const float* x,
                                      const float* weights, const float* kernel_points, const float* grad_out, int64_t n_q,
                                      int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out, float kp_extent, int influence,
-                                     int aggregation, float* d_x, float* d_weights, void* workspace, size_t workspace_bytes,
-                                     void* stream_) {
+                                     int aggregation, const int32_t* order, float* d_x, float* d_weights, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
   int rc = check_kpconv_args(n_q, n_s, n_nbrs, n_kpts, c_in, c_out, kp_extent, influence, aggregation);
   if (rc) return rc;
   if (!d_weights || !weights || !kernel_points || !workspace) return KPREG_E_INVALID;
@@ -611,9 +616,9 @@ extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, con
   k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, w.row_pos);
   KP_LAUNCH_CHECK();
   rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                      influence, aggregation, w.agg, w.inv_num, stream)
+                                      influence, aggregation, w.agg, w.inv_num, order, stream)
              : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                      influence, aggregation, w.agg, w.inv_num, stream);
+                                      influence, aggregation, w.agg, w.inv_num, order, stream);
   if (rc) return rc;
   // g' = grad_out / num
   {
@@ -635,7 +640,7 @@ extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, con
   rc = launch_gemm<false, true>(w.g_scaled, weights, w.d_agg, nullptr, n_q, kd, c_out, 1, stream);
   if (rc) return rc;
   return idx64 ? launch_scatter<int64_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                         influence, aggregation, d_x, stream)
+                                         influence, aggregation, d_x, order, stream)
                : launch_scatter<int32_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
-                                         influence, aggregation, d_x, stream);
+                                         influence, aggregation, d_x, order, stream);
 }

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
     const GridHeader* __restrict__ hdr, const int64_t* __restrict__ s_off, int n_clouds, int64_t n_supports,
     const float4* __restrict__ sorted, const uint64_t* __restrict__ tab_key, const int2* __restrict__ tab_val, uint32_t cap,
     const float* __restrict__ queries, const int64_t* __restrict__ q_off, int64_t n_queries, float radius, float r2, int width,
-    OutT* __restrict__ out, int32_t* __restrict__ out_counts, int32_t* __restrict__ out_stats) {
+    OutT* __restrict__ out, int32_t* __restrict__ out_counts, int32_t* __restrict__ out_stats, const int32_t* __restrict__ order) {
   __shared__ unsigned long long s_hits[kWarpsPerBlock][kHitCap];
   __shared__ int s_cell_start[kWarpsPerBlock][32];
   __shared__ int s_cell_prefix[kWarpsPerBlock][32];
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
   int my_max = 0;
   unsigned long long* hits = s_hits[warp];
 
-  for (int64_t qi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; qi < n_queries; qi += (int64_t)gridDim.x * kWarpsPerBlock) {
+  for (int64_t it = (int64_t)blockIdx.x * kWarpsPerBlock + warp; it < n_queries; it += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t qi = order ? (int64_t)order[it] : it;  // processing order only (cell-sorted queries share cells)
     const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
     const int cloud = cloud_of(q_off, n_clouds, qi);
     const int64_t cloud_base = s_off[cloud];
@@ -352,7 +353,7 @@ extern "C" int kpreg_grid_workspace_bytes(int64_t n_supports, int n_clouds, size
 }
 
 extern "C" int kpreg_grid_build(const float* supports, const int32_t* s_lens, int64_t n, int n_clouds, float cell,
-                                void* grid, size_t grid_bytes, void* stream_) {
+                                void* grid, size_t grid_bytes, int32_t* out_order, void* stream_) {
   if (!s_lens || !grid || n < 0 || n_clouds < 1 || !(cell > 0.f)) return KPREG_E_INVALID;
   if (n > 0 && !supports) return KPREG_E_INVALID;
   if (n >= (int64_t)0x7fffffff || n_clouds >= (1 << (63 - kCloudShift))) return KPREG_E_INVALID;
@@ -386,12 +387,14 @@ extern "C" int kpreg_grid_build(const float* supports, const int32_t* s_lens, in
   count_launches((unsigned long long)(2 + (end_bit + 7) / 8));
   k_grid_fill<<<blocks, 256, 0, stream>>>(supports, w.off, dk.Current(), dv.Current(), n, w.sorted, w.tab_key, w.tab_val, w.tab_cap);
   KP_LAUNCH_CHECK();
+  if (out_order)  // the cell-sorted permutation of the supports: a spatially coherent processing order for later kernels
+    KP_CUDA_TRY(cudaMemcpyAsync(out_order, dv.Current(), sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
   return KPREG_OK;
 }
 
 extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const float* queries, const int32_t* q_lens,
-                                int64_t n_queries, float radius, int width, int idx64, void* out_idx, int32_t* out_counts,
-                                int32_t* out_stats, void* stream_) {
+                                int64_t n_queries, float radius, int width, int idx64, const int32_t* order, void* out_idx,
+                                int32_t* out_counts, int32_t* out_stats, void* stream_) {
   if (!grid || !q_lens || !out_stats || n < 0 || n_clouds < 1 || n_queries < 0 || width < 0 || !(radius > 0.f)) return KPREG_E_INVALID;
   if (n_queries == 0) return KPREG_OK;
   if (!queries || (width > 0 && !out_idx)) return KPREG_E_INVALID;
@@ -408,11 +411,11 @@ extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const
   if (idx64) {
     k_grid_query<int64_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
                                                                      w.tab_cap, queries, q_off, n_queries, radius, r2, width,
-                                                                     static_cast<int64_t*>(out_idx), out_counts, out_stats);
+                                                                     static_cast<int64_t*>(out_idx), out_counts, out_stats, order);
   } else {
     k_grid_query<int32_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
                                                                      w.tab_cap, queries, q_off, n_queries, radius, r2, width,
-                                                                     static_cast<int32_t*>(out_idx), out_counts, out_stats);
+                                                                     static_cast<int32_t*>(out_idx), out_counts, out_stats, order);
   }
   KP_LAUNCH_CHECK();
   return KPREG_OK;

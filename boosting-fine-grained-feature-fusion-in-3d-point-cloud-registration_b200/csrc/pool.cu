@@ -10,10 +10,12 @@ namespace {
 
 template <typename IdxT>
 __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, const IdxT* __restrict__ idx, int64_t n_q, int64_t n_s,
-                                                  int n_nbrs, int channels, float* __restrict__ out, int32_t* __restrict__ argmax) {
+                                                  int n_nbrs, int channels, float* __restrict__ out, int32_t* __restrict__ argmax,
+                                                  const int32_t* __restrict__ order) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= n_q) return;
+  const int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (it >= n_q) return;
+  const int64_t n = order ? (int64_t)order[it] : it;  // processing order only
   for (int c0 = 0; c0 < channels; c0 += 32) {
     const int c = c0 + lane;
     float best = -3.402823466e38f;
@@ -54,15 +56,15 @@ __global__ void __launch_bounds__(256) k_max_pool_bwd(const float* __restrict__ 
 using namespace kpreg;
 
 extern "C" int kpreg_max_pool_forward(const float* x, const void* idx, int idx64, int64_t n_q, int64_t n_s, int n_nbrs,
-                                      int channels, float* out, int32_t* argmax, void* stream_) {
+                                      int channels, const int32_t* order, float* out, int32_t* argmax, void* stream_) {
   if (n_q < 0 || n_s < 0 || n_nbrs < 0 || channels < 1) return KPREG_E_INVALID;
   if (n_q == 0) return KPREG_OK;
   if (!out || (n_nbrs > 0 && !idx) || (n_s > 0 && !x)) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int blocks = ceil_div(n_q * 32, 256);
   ProfScope prof(KPREG_FAM_POOL, stream);
-  if (idx64) k_max_pool<int64_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax);
-  else k_max_pool<int32_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax);
+  if (idx64) k_max_pool<int64_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+  else k_max_pool<int32_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }

@@ -85,23 +85,24 @@ class Preprocessor(nn.Module):
         stats = torch.zeros((n_tables_max, 2), dtype=torch.int32, device=dev)
         next_slot = [0]
 
-        def query(grid, q_pts, q_lens, radius, limit):
+        def query(grid, q_pts, q_lens, radius, limit, order=None):
             slot = next_slot[0]
             next_slot[0] += 1
             if limit > 0:
-                rows, _, _ = grid.query(q_pts, q_lens, radius, limit, stats=stats[slot])
+                rows, _, _ = grid.query(q_pts, q_lens, radius, limit, stats=stats[slot], order=order)
                 return _Table(rows, limit, slot)
             # no limit: the width itself is data dependent -> count first (one extra read-back)
-            _, _, st = grid.query(q_pts, q_lens, radius, 0, stats=stats[slot])
+            _, _, st = grid.query(q_pts, q_lens, radius, 0, stats=stats[slot], order=order)
             width = int(st[0].item())
-            rows, _, _ = grid.query(q_pts, q_lens, radius, max(width, 1), stats=stats[slot])
+            rows, _, _ = grid.query(q_pts, q_lens, radius, max(width, 1), stats=stats[slot], order=order)
             return _Table(rows, max(width, 1), slot)
 
         r_normal = cfg.first_subsampling_dl * cfg.conv_radius
-        level_points, level_lens = [], []
+        level_points, level_lens, level_orders = [], [], []
         conv_tabs, pool_tabs, up_tabs = [], [], []
         layer_blocks, layer = [], 0
-        pending_up = None  # (fine points, fine lens, radius, limit): answered by the next level's grid
+        grid = None           # cell grid of the current level (built one level ahead, see below)
+        pending_up = None     # (fine points, fine lens, radius, limit, fine order): answered by the next level's grid
 
         for block_i, block in enumerate(arch):
             if 'global' in block or 'upsample' in block:
@@ -116,18 +117,22 @@ class Preprocessor(nn.Module):
             r_conv = r_normal * cfg.deform_radius / cfg.conv_radius if deform_conv else r_normal
             r_pool = r_normal * cfg.deform_radius / cfg.conv_radius if 'deformable' in block else r_normal
             # one cell grid per level serves the conv table, the pool table (coarse queries) and the previous
-            # level's upsample table (fine queries, radius 2*r_prev = r of this level)
+            # level's upsample table (fine queries, radius 2*r_prev = r of this level); its cell-sorted permutation
+            # doubles as the spatially coherent processing order of this level's rows (batch['orders'])
             cell = max(r_conv if layer_blocks else 0.0, r_pool if strided else 0.0,
                        pending_up[2] if pending_up is not None else 0.0)
-            grid = ops.CellGrid(points, lens, cell) if cell > 0 else None
+            if grid is None or grid.cell < cell:
+                grid = ops.CellGrid(points, lens, cell) if cell > 0 else None
+            order = grid.order if grid is not None else None
 
             if pending_up is not None:
-                up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3]))
+                up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3], pending_up[4]))
                 pending_up = None
-            conv_tabs.append(query(grid, points, lens, r_conv, limits[layer]) if layer_blocks else None)
+            conv_tabs.append(query(grid, points, lens, r_conv, limits[layer], order) if layer_blocks else None)
 
             level_points.append(points)
             level_lens.append(lens)
+            level_orders.append(order)
             if strided:
                 dl = 2 * r_normal / cfg.conv_radius
                 sub, counts = ops.subsample(points, lens, dl)
@@ -138,23 +143,27 @@ class Preprocessor(nn.Module):
                 if m < 1:
                     raise RuntimeError("Error")
                 pool_p, pool_b = sub[:m], counts[:n_clouds]
-                pool_tabs.append(query(grid, pool_p, pool_b, r_pool, limits[layer]))
-                pending_up = (points, lens, 2 * r_pool, limits[layer])
-                points, lens = pool_p, pool_b
+                # the next level's grid is built now (cell = its conv radius = 2 r) so that its order can already
+                # drive the pool query of the coarse points against this level's grid
+                next_grid = ops.CellGrid(pool_p, pool_b, 2 * r_pool)
+                pool_tabs.append(query(grid, pool_p, pool_b, r_pool, limits[layer], next_grid.order))
+                pending_up = (points, lens, 2 * r_pool, limits[layer], order)
+                points, lens, grid = pool_p, pool_b, next_grid
             else:
                 pool_tabs.append(None)
                 up_tabs.append(None)
+                grid = None
             r_normal *= 2
             layer += 1
             layer_blocks = []
 
         if pending_up is not None:
             # architecture ended on a strided block: the upsample table still needs the coarse grid
-            grid = ops.CellGrid(points, lens, pending_up[2])
-            up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3]))
+            up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3], pending_up[4]))
             pending_up = None
             level_points.append(points)
             level_lens.append(lens)
+            level_orders.append(grid.order if grid is not None else None)
             conv_tabs.append(None)
             pool_tabs.append(None)
             up_tabs.append(None)
@@ -184,7 +193,10 @@ class Preprocessor(nn.Module):
             'stack_lengths': level_lens,
         }
         if in_device.type != "cuda":
-            data = {k: [t.to(in_device) for t in v] for k, v in data.items()}
+            return {k: [t.to(in_device) for t in v] for k, v in data.items()}
+        # extra key (not in the reference's dict): per level, the cell-sorted permutation of its rows — the blocks
+        # hand it to the CUDA kernels as a processing order; consumers that do not know the key are unaffected
+        data['orders'] = level_orders
         return data
 
 

@@ -49,8 +49,8 @@ def gather(x, idx, method=2):
 
 class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, inds):
-        out, arg = ops.max_pool_forward(x, inds, want_argmax=ctx.needs_input_grad[0])
+    def forward(ctx, x, inds, order=None):
+        out, arg = ops.max_pool_forward(x, inds, want_argmax=ctx.needs_input_grad[0], order=order)
         ctx.n_s = x.shape[0]
         if arg is not None:
             ctx.save_for_backward(arg)
@@ -59,12 +59,13 @@ class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (arg,) = ctx.saved_tensors
-        return ops.max_pool_backward(grad.contiguous(), arg, ctx.n_s), None
+        return ops.max_pool_backward(grad.contiguous(), arg, ctx.n_s), None, None
 
 
-def max_pool(x, inds):
-    """[n2, d] = max over the pooling rows of [x; 0] (the zero shadow row takes part)."""
-    return _MaxPoolFn.apply(x, inds)
+def max_pool(x, inds, order=None):
+    """[n2, d] = max over the pooling rows of [x; 0] (the zero shadow row takes part).
+    ``order`` (optional, not in the reference): processing-order permutation of the pooled rows."""
+    return _MaxPoolFn.apply(x, inds, order)
 
 
 def closest_pool(x, inds):
@@ -83,20 +84,21 @@ def global_average(x, batch_lengths):
 
 class _KPConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, influence, aggregation, gemm):
+    def forward(ctx, q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, influence, aggregation, gemm, order):
         ctx.save_for_backward(q_pts, s_pts, neighb_inds, x, weights, kernel_points)
         ctx.cfg = (extent, influence, aggregation)
+        ctx.order = order
         return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, influence,
-                                  aggregation, gemm)
+                                  aggregation, gemm, order)
 
     @staticmethod
     def backward(ctx, grad_out):
         q_pts, s_pts, neighb_inds, x, weights, kernel_points = ctx.saved_tensors
         extent, influence, aggregation = ctx.cfg
         d_x, d_w = ops.kpconv_backward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, grad_out.contiguous(),
-                                       extent, influence, aggregation)
+                                       extent, influence, aggregation, ctx.order)
         # coordinates, indices and kernel points carry no gradient (reference :262-263)
-        return None, None, None, d_x, d_w, None, None, None, None, None
+        return None, None, None, d_x, d_w, None, None, None, None, None, None
 
 
 class KPConv(nn.Module):
@@ -133,10 +135,12 @@ class KPConv(nn.Module):
     def reset_parameters(self):
         nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
 
-    def forward(self, q_pts, s_pts, neighb_inds, x):
+    def forward(self, q_pts, s_pts, neighb_inds, x, order=None):
+        """``order`` (optional, not in the reference): int32 permutation of the query rows giving a spatially
+        coherent processing order (Preprocessor's batch['orders']); it never changes the result."""
         gemm = DEFAULT_GEMM if self.gemm is None else self.gemm
         return _KPConvFn.apply(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points, float(self.KP_extent),
-                               self.KP_influence, self.aggregation_mode, gemm)
+                               self.KP_influence, self.aggregation_mode, gemm, order)
 
     def __repr__(self):
         return 'KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
@@ -244,12 +248,18 @@ class UnaryBlock2(nn.Module):
 
 
 def _conv_inputs(batch, layer_ind, strided):
-    """(q_pts, s_pts, neighb_inds, stack_lengths of the output level) for a block at pyramid level layer_ind."""
+    """(q_pts, s_pts, neighb_inds, stack_lengths of the output level, processing order of the query rows or None)
+    for a block at pyramid level layer_ind."""
+    orders = batch.get('orders') if hasattr(batch, 'get') else None
+    q_level = layer_ind + 1 if strided else layer_ind
+    order = orders[q_level] if orders is not None and q_level < len(orders) else None
+    if order is not None and not order.is_cuda:
+        order = None
     if strided:
         return (batch['points'][layer_ind + 1], batch['points'][layer_ind], batch['pools'][layer_ind],
-                batch['stack_lengths'][layer_ind + 1])
+                batch['stack_lengths'][layer_ind + 1], order)
     return (batch['points'][layer_ind], batch['points'][layer_ind], batch['neighbors'][layer_ind],
-            batch['stack_lengths'][layer_ind])
+            batch['stack_lengths'][layer_ind], order)
 
 
 def _make_kpconv(in_dim, out_dim, radius, config, block_name):
@@ -276,8 +286,8 @@ class SimpleBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1)
 
     def forward(self, x, batch):
-        q_pts, s_pts, inds, lens = _conv_inputs(batch, self.layer_ind, 'strided' in self.block_name)
-        return self.batch_norm(self.KPConv(q_pts, s_pts, inds, x), lens, act="leaky_relu")
+        q_pts, s_pts, inds, lens, order = _conv_inputs(batch, self.layer_ind, 'strided' in self.block_name)
+        return self.batch_norm(self.KPConv(q_pts, s_pts, inds, x, order), lens, act="leaky_relu")
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -303,14 +313,14 @@ class ResnetBottleneckBlock(nn.Module):
 
     def forward(self, features, batch):
         strided = 'strided' in self.block_name
-        q_pts, s_pts, inds, lens_post = _conv_inputs(batch, self.layer_ind, strided)
+        q_pts, s_pts, inds, lens_post, order = _conv_inputs(batch, self.layer_ind, strided)
         lens_pre = batch['stack_lengths'][self.layer_ind]
 
         x = self.unary1(features, lens_pre) if isinstance(self.unary1, UnaryBlock) else features
-        x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x), lens_post)
+        x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)
         x = self.leaky_relu(self.res2net(x))
 
-        shortcut = max_pool(features, inds) if strided else features
+        shortcut = max_pool(features, inds, order) if strided else features
         if isinstance(self.unary_shortcut, UnaryBlock):
             # leaky_relu(x + norm(mlp(shortcut))): the addition and activation ride on the norm kernel when fused
             return self.unary_shortcut(shortcut, lens_post, residual=x, final_act=True)

@@ -70,7 +70,7 @@ class CellGrid:
     """Supports binned into cells of edge ``cell`` (kpreg_grid_build); serves radius queries with
     radius <= cell for any query set of the same batch (kpreg_grid_query)."""
 
-    def __init__(self, supports: torch.Tensor, s_lens: torch.Tensor, cell: float):
+    def __init__(self, supports: torch.Tensor, s_lens: torch.Tensor, cell: float, want_order: bool = True):
         lib = _lib.load()
         self.supports = _f32c(supports, "supports")
         self.s_lens = _i32c(s_lens, "s_batches")
@@ -80,12 +80,16 @@ class CellGrid:
         dev = self.supports.device
         nbytes = _lib.size_query("kpreg_grid_workspace_bytes", self.n, self.n_clouds)
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # cell-sorted permutation of the supports: a spatially coherent processing order for later kernels
+        self.order = torch.empty(self.n, dtype=torch.int32, device=dev) if want_order and self.n > 0 else None
         rc = lib.kpreg_grid_build(self.supports.data_ptr(), self.s_lens.data_ptr(), self.n, self.n_clouds,
-                                  self.cell, self.buf.data_ptr(), self.buf.numel(), _lib.stream_ptr(dev))
+                                  self.cell, self.buf.data_ptr(), self.buf.numel(), _lib.ptr(self.order),
+                                  _lib.stream_ptr(dev))
         _lib.check(rc, "kpreg_grid_build")
 
     def query(self, queries: torch.Tensor, q_lens: torch.Tensor, radius: float, width: int,
-              stats: Optional[torch.Tensor] = None, want_counts: bool = False, idx64: bool = False):
+              stats: Optional[torch.Tensor] = None, want_counts: bool = False, idx64: bool = False,
+              order: Optional[torch.Tensor] = None):
         """Rows of ascending-(d2, index) neighbours, truncated/padded to ``width`` columns.
 
         Returns (idx [Nq,width], counts [Nq] or None, stats int32 [2] = {max count, status})."""
@@ -101,10 +105,19 @@ class CellGrid:
         if stats is None:
             stats = torch.zeros(2, dtype=torch.int32, device=dev)
         rc = lib.kpreg_grid_query(self.buf.data_ptr(), self.n, self.n_clouds, queries.data_ptr(), q_lens.data_ptr(),
-                                  nq, float(radius), int(width), 1 if idx64 else 0, out.data_ptr(),
-                                  _lib.ptr(counts), stats.data_ptr(), _lib.stream_ptr(dev))
+                                  nq, float(radius), int(width), 1 if idx64 else 0, _order_ptr(order, nq),
+                                  out.data_ptr(), _lib.ptr(counts), stats.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "kpreg_grid_query")
         return out, counts, stats
+
+
+def _order_ptr(order: Optional[torch.Tensor], n_rows: int):
+    """Pointer of an optional int32 processing-order permutation of n_rows query rows."""
+    if order is None:
+        return None
+    if not order.is_cuda or order.dtype != torch.int32 or order.numel() != n_rows or not order.is_contiguous():
+        raise RuntimeError("order must be a contiguous int32 CUDA permutation of the query rows")
+    return order.data_ptr()
 
 
 def pack_rows(rows: torch.Tensor, out_width: int, idx64: bool) -> torch.Tensor:
@@ -125,7 +138,7 @@ def pack_rows(rows: torch.Tensor, out_width: int, idx64: bool) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 
 def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: float, influence: str = "linear",
-                   aggregation: str = "sum", gemm: int = 0) -> torch.Tensor:
+                   aggregation: str = "sum", gemm: int = 0, order: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     if influence not in INFLUENCE:
         raise ValueError("Unknown influence function type (config.KP_influence)")
@@ -145,13 +158,13 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     rc = lib.kpreg_kpconv_forward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
                                   weights.data_ptr(), kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
                                   float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation], int(gemm),
-                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+                                  _order_ptr(order, n_q), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_kpconv_forward")
     return out
 
 
 def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_extent: float,
-                    influence: str = "linear", aggregation: str = "sum"):
+                    influence: str = "linear", aggregation: str = "sum", order: Optional[torch.Tensor] = None):
     """Returns (d_x [n_s,c_in], d_weights [K,c_in,c_out])."""
     lib = _lib.load()
     q_pts, s_pts, x = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
@@ -168,7 +181,8 @@ def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_e
     rc = lib.kpreg_kpconv_backward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
                                    weights.data_ptr(), kernel_points.data_ptr(), grad_out.data_ptr(), n_q, n_s, h, k,
                                    c_in, c_out, float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation],
-                                   d_x.data_ptr(), d_w.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+                                   _order_ptr(order, n_q), d_x.data_ptr(), d_w.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_kpconv_backward")
     return d_x, d_w
 
@@ -177,7 +191,7 @@ def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_e
 # max pool
 # ------------------------------------------------------------------------------------------------
 
-def max_pool_forward(x, idx, want_argmax: bool = False):
+def max_pool_forward(x, idx, want_argmax: bool = False, order: Optional[torch.Tensor] = None):
     lib = _lib.load()
     x = _f32c(x, "x")
     idx, idx64 = _idx(idx, "inds")
@@ -185,8 +199,8 @@ def max_pool_forward(x, idx, want_argmax: bool = False):
     n_q, h = idx.shape
     out = torch.empty((n_q, c), dtype=torch.float32, device=x.device)
     arg = torch.empty((n_q, c), dtype=torch.int32, device=x.device) if want_argmax else None
-    rc = lib.kpreg_max_pool_forward(x.data_ptr(), idx.data_ptr(), idx64, n_q, n_s, h, c, out.data_ptr(),
-                                    _lib.ptr(arg), _lib.stream_ptr(x.device))
+    rc = lib.kpreg_max_pool_forward(x.data_ptr(), idx.data_ptr(), idx64, n_q, n_s, h, c, _order_ptr(order, n_q),
+                                    out.data_ptr(), _lib.ptr(arg), _lib.stream_ptr(x.device))
     _lib.check(rc, "kpreg_max_pool_forward")
     return out, arg
 

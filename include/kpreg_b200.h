@@ -98,13 +98,18 @@ KPREG_API int kpreg_subsample_batch(const float* pts, const int32_t* lens, int64
  *   out_counts  optional [n_queries] int32: untruncated neighbour count per query
  *   out_stats   [2] int32, accumulated with max: {max untruncated count, status}; zero it first.
  * The reference's row width is min(out_stats[0], limit).
+ *
+ * Processing order.  kpreg_grid_build can return the cell-sorted permutation of its supports (out_order,
+ * int32 [n_supports], may be NULL).  kpreg_grid_query, kpreg_kpconv_forward/backward and kpreg_max_pool_forward
+ * accept such a permutation of their QUERY rows as `order` (may be NULL): it only changes which warp handles which
+ * row — spatially adjacent queries share neighbours, which turns L2 gathers into L1 hits — never the results.
  * ------------------------------------------------------------------------------------------- */
 KPREG_API int kpreg_grid_workspace_bytes(int64_t n_supports, int n_clouds, size_t* bytes);
 KPREG_API int kpreg_grid_build(const float* supports, const int32_t* s_lens, int64_t n_supports, int n_clouds,
-                     float cell, void* grid, size_t grid_bytes, void* stream);
+                     float cell, void* grid, size_t grid_bytes, int32_t* out_order, void* stream);
 KPREG_API int kpreg_grid_query(const void* grid, int64_t n_supports, int n_clouds, const float* queries,
                      const int32_t* q_lens, int64_t n_queries, float radius, int width, int idx64,
-                     void* out_idx, int32_t* out_counts, int32_t* out_stats, void* stream);
+                     const int32_t* order, void* out_idx, int32_t* out_counts, int32_t* out_stats, void* stream);
 /* Re-pack [n_rows, in_width] int32 rows to [n_rows, out_width] (out_width <= in_width), int32 or int64. */
 KPREG_API int kpreg_pack_rows(const int32_t* in, int64_t n_rows, int in_width, int out_width, int idx64,
                     void* out, void* stream);
@@ -126,14 +131,14 @@ KPREG_API int kpreg_kpconv_workspace_bytes(int64_t n_q, int64_t n_s, int n_kpts,
 KPREG_API int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, const void* idx, int idx64,
                          const float* x, const float* weights, const float* kernel_points,
                          int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out,
-                         float kp_extent, int influence, int aggregation, int gemm, float* out,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         float kp_extent, int influence, int aggregation, int gemm, const int32_t* order,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
 KPREG_API int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, const void* idx, int idx64,
                           const float* x, const float* weights, const float* kernel_points,
                           const float* grad_out, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
                           int c_in, int c_out, float kp_extent, int influence, int aggregation,
-                          float* d_x, float* d_weights, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          const int32_t* order, float* d_x, float* d_weights, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Strided-block shortcut pooling.
@@ -142,7 +147,8 @@ KPREG_API int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, cons
  *   argmax [n_q,c] int32 receives the winning support row (n_s for the shadow row); may be NULL.
  * ------------------------------------------------------------------------------------------- */
 KPREG_API int kpreg_max_pool_forward(const float* x, const void* idx, int idx64, int64_t n_q, int64_t n_s,
-                           int n_nbrs, int channels, float* out, int32_t* argmax, void* stream);
+                           int n_nbrs, int channels, const int32_t* order, float* out, int32_t* argmax,
+                           void* stream);
 KPREG_API int kpreg_max_pool_backward(const float* grad_out, const int32_t* argmax, int64_t n_q, int64_t n_s,
                             int channels, float* d_x, void* stream);
 
