@@ -176,10 +176,24 @@ NormWs carve_norm(void* base, int n_clouds, int channels) {
 
 using namespace kpreg;
 
+extern "C" int kpreg_gemm_supported(int64_t m_rows, int k_dim, int n_dim, int ldx, const void* x) {
+  return gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x) ? 1 : 0;
+}
+
 extern "C" int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes) {
   if (!bytes || k_dim < 1 || n_dim < 1) return KPREG_E_INVALID;
   *bytes = kpconv_gemm_tc_weight_bytes(k_dim, n_dim) + 256;
   return KPREG_OK;
+}
+
+// Split a weight matrix once (inference: weights do not change between calls) into the hi/lo TF32 operand pair
+// the tensor-core GEMM consumes.  weight is [n_dim, k_dim] (transpose = 0, nn.Linear) or [k_dim, n_dim]
+// (transpose = 1, KPConv's [K*c_in, c_out]).  out must hold kpreg_linear_workspace_bytes(k_dim, n_dim) bytes.
+extern "C" int kpreg_split_weights(const float* weight, int k_dim, int n_dim, int transpose, void* out, size_t out_bytes,
+                                   void* stream_) {
+  if (!weight || !out || k_dim < 1 || n_dim < 1) return KPREG_E_INVALID;
+  if (out_bytes < kpconv_gemm_tc_weight_bytes(k_dim, n_dim)) return KPREG_E_WORKSPACE;
+  return kpconv_gemm_tc_prepare_weights(weight, k_dim, n_dim, transpose ? 1 : 0, static_cast<float*>(out), (cudaStream_t)stream_);
 }
 
 extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
@@ -191,6 +205,12 @@ extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight
   if (!x || !weight || !out || (out2 && !addend)) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   ProfScope prof(KPREG_FAM_LINEAR, stream);
+  if (gemm == 2) {
+    // `weight` already is the split operand pair produced by kpreg_split_weights
+    if (!gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x)) return KPREG_E_INVALID;
+    return launch_gemm_tc(x, ldx, weight, out, ldc, m_rows, k_dim, n_dim, nullptr, col_scale, col_shift, residual, ld_res, act,
+                          slope, out2, ld2, addend, ld_add, stream);
+  }
   if (gemm == 1 && gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x)) {
     if (!workspace || workspace_bytes < kpconv_gemm_tc_weight_bytes(k_dim, n_dim)) return KPREG_E_WORKSPACE;
     float* w_split = static_cast<float*>(workspace);

@@ -584,6 +584,12 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   if (rc) return rc;
   const int kd = n_kpts * c_in;
   ProfScope prof(KPREG_FAM_CONTRACT, stream);
+  if (gemm == 2) {
+    // `weights` already is the split operand pair produced by kpreg_split_weights(transpose = 1)
+    if (!gemm_tc_supported(n_q, kd, c_out, kd, w.agg)) return KPREG_E_INVALID;
+    return launch_gemm_tc(w.agg, kd, weights, out, c_out, n_q, kd, c_out, w.inv_num, nullptr, nullptr, nullptr, 0, 0, 0.f,
+                          nullptr, 0, nullptr, 0, stream);
+  }
   if (gemm == 1 && gemm_tc_supported(n_q, kd, c_out, kd, w.agg)) {
     rc = kpconv_gemm_tc_prepare_weights(weights, kd, c_out, 1, w.w_split, stream);
     if (rc) return rc;

@@ -7,6 +7,7 @@ neighbour row widths) are returned as small device tensors; the callers in ``cpp
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -145,6 +146,7 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     if aggregation not in AGGREGATION:
         raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
     q_pts, s_pts, x = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
+    weights_in = weights
     weights, kernel_points = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
     idx, idx64 = _idx(idx, "neighb_inds")
     n_q, n_s, h = q_pts.shape[0], s_pts.shape[0], idx.shape[1] if idx.dim() == 2 else 0
@@ -155,8 +157,11 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     out = torch.empty((n_q, c_out), dtype=torch.float32, device=dev)
     nbytes = _lib.size_query("kpreg_kpconv_workspace_bytes", n_q, n_s, k, c_in, c_out, 0)
     ws = _lib.workspaces.get(nbytes, dev)
+    w_ptr = weights.data_ptr()
+    if gemm == 1 and not torch.is_grad_enabled() and (k * c_in) % 4 == 0 and k * c_in >= 4 and c_out >= 8 and n_q > 0:
+        w_ptr, gemm = cached_split(weights_in, True).buf.data_ptr(), 2  # inference: the weights were split once
     rc = lib.kpreg_kpconv_forward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
-                                  weights.data_ptr(), kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
+                                  w_ptr, kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
                                   float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation], int(gemm),
                                   _order_ptr(order, n_q), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_kpconv_forward")
@@ -247,6 +252,42 @@ def kabsch(a: torch.Tensor, b: torch.Tensor, w: Optional[torch.Tensor], n_sets: 
 ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2}
 
 
+class SplitWeights:
+    """hi/lo TF32 operand pair of a weight matrix, produced once by kpreg_split_weights (inference)."""
+
+    def __init__(self, weight: torch.Tensor, transpose: bool):
+        lib = _lib.load()
+        w = _f32c(weight, "weight")
+        if transpose:  # KPConv weights [K, c_in, c_out] -> [K*c_in, c_out]
+            w = w.reshape(-1, w.shape[-1])
+            self.k, self.n = int(w.shape[0]), int(w.shape[1])
+        else:
+            self.n, self.k = int(w.shape[0]), int(w.shape[1])
+        nbytes = _lib.size_query("kpreg_linear_workspace_bytes", self.k, self.n)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        rc = lib.kpreg_split_weights(w.data_ptr(), self.k, self.n, 1 if transpose else 0, self.buf.data_ptr(), nbytes,
+                                     _lib.stream_ptr(w.device))
+        _lib.check(rc, "kpreg_split_weights")
+
+
+_SPLIT_CACHE: dict = {}
+
+
+def cached_split(weight: torch.Tensor, transpose: bool) -> SplitWeights:
+    """Split-weight cache for inference.  An entry is valid only for the very same tensor object (checked through
+    a weak reference, so a recycled address can never alias) at the same version counter (in-place updates by an
+    optimizer or load_state_dict bump it)."""
+    key = (id(weight), bool(transpose))
+    hit = _SPLIT_CACHE.get(key)
+    if hit is None or hit[0]() is not weight or hit[1] != weight._version:
+        if len(_SPLIT_CACHE) > 4096:
+            for k in [k for k, v in _SPLIT_CACHE.items() if v[0]() is None]:
+                del _SPLIT_CACHE[k]
+        hit = (weakref.ref(weight), weight._version, SplitWeights(weight, transpose))
+        _SPLIT_CACHE[key] = hit
+    return hit[2]
+
+
 def _rows(t: torch.Tensor, name: str):
     """(tensor, row pitch) of a 2-D fp32 CUDA tensor whose rows are contiguous (column slices are fine)."""
     _lib.require_cuda(t, name)
@@ -261,8 +302,11 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     ``out`` may be a column slice of a wider buffer; ``out2`` (optional) receives out + addend."""
     lib = _lib.load()
     x, ldx = _rows(x, "x")
-    weight = _f32c(weight, "weight")
     m, k = x.shape
+    presplit = None
+    if gemm == 1 and not torch.is_grad_enabled() and lib.kpreg_gemm_supported(m, k, int(weight.shape[0]), ldx, x.data_ptr()):
+        presplit = cached_split(weight, False)  # inference: the weights were split once
+    weight = _f32c(weight, "weight")
     n = weight.shape[0]
     if weight.shape[1] != k:
         raise RuntimeError("linear: inconsistent shapes")
@@ -282,9 +326,10 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     cb = None if col_shift is None else _f32c(col_shift, "col_shift")
     nbytes = _lib.size_query("kpreg_linear_workspace_bytes", k, n)
     ws = _lib.workspaces.get(nbytes, dev)
-    rc = lib.kpreg_linear_forward(x.data_ptr(), ldx, weight.data_ptr(), m, k, n, _lib.ptr(cs), _lib.ptr(cb), res_ptr, ld_res,
-                                  ACT[act], float(slope), out.data_ptr(), ldc, o2_ptr, ld2, add_ptr, ld_add, int(gemm),
-                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    w_ptr = presplit.buf.data_ptr() if presplit is not None else weight.data_ptr()
+    rc = lib.kpreg_linear_forward(x.data_ptr(), ldx, w_ptr, m, k, n, _lib.ptr(cs), _lib.ptr(cb), res_ptr, ld_res,
+                                  ACT[act], float(slope), out.data_ptr(), ldc, o2_ptr, ld2, add_ptr, ld_add,
+                                  2 if presplit is not None else int(gemm), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_linear_forward")
     return out
 

@@ -179,7 +179,16 @@ KPREG_API int kpreg_kabsch(const float* a, const float* b, float* w, const int64
  *   Replaces BatchNormBlock's per-cloud nn.InstanceNorm1d (finegrained_kpconv_blocks.py:462-518; biased variance,
  *   eps inside the square root, no affine, no running statistics), optionally fused with the activation and the
  *   shortcut addition that follow it in the blocks.  channels, ldx, ldo, ld_res must be multiples of 4.
- * ------------------------------------------------------------------------------------------- */
+ *
+ * kpreg_split_weights: for inference, split a weight matrix ONCE into the hi/lo TF32 operand pair of the tensor-core
+ *   GEMM ([n_dim,k_dim] with transpose = 0, or KPConv's [K*c_in, c_out] with transpose = 1; `out` holds
+ *   kpreg_linear_workspace_bytes(k_dim, n_dim) bytes).  Passing that buffer as `weight` / `weights` together with
+ *   gemm = 2 to kpreg_linear_forward / kpreg_kpconv_forward skips the per-call split.  kpreg_gemm_supported tells
+ *   whether a shape is addressable by the TMA path (K >= 4, row pitch and base 16-byte aligned, N >= 8).
+ */
+KPREG_API int kpreg_split_weights(const float* weight, int k_dim, int n_dim, int transpose, void* out, size_t out_bytes,
+                                  void* stream);
+KPREG_API int kpreg_gemm_supported(int64_t m_rows, int k_dim, int n_dim, int ldx, const void* x);
 KPREG_API int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes);
 KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
                                    const float* col_scale, const float* col_shift, const float* residual, int ld_res,
