@@ -318,7 +318,11 @@ class ResnetBottleneckBlock(nn.Module):
 
         x = self.unary1(features, lens_pre) if isinstance(self.unary1, UnaryBlock) else features
         x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)
-        x = self.leaky_relu(self.res2net(x))
+        x = self.res2net(x)
+        if not _fused(x):
+            # my_Bottle2neck ends in a ReLU, so this LeakyReLU is the identity; kept on the autograd path only so
+            # that the graph matches the reference op for op
+            x = self.leaky_relu(x)
 
         shortcut = max_pool(features, inds, order) if strided else features
         if isinstance(self.unary_shortcut, UnaryBlock):

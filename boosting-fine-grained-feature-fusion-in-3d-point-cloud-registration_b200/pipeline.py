@@ -18,6 +18,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .kpconv import KPFEncoder, Preprocessor
 from .se3_torch import compute_rigid_transform_batch, se3_compare
 
@@ -75,6 +76,48 @@ def synthetic_correspondences(coarse_pts: torch.Tensor, coarse_lens: Sequence[in
     return a_all, b_all, w_all
 
 
+def synthetic_correspondences_batched(coarse_pts: torch.Tensor, coarse_lens: torch.Tensor, poses: torch.Tensor,
+                                      noise: float = 0.01, seed: int = 0):
+    """Same construction as synthetic_correspondences for ALL pairs at once, entirely on the device and without
+    a host read-back (a handful of launches whatever the batch size).  Returns (a, b [T,3], w [T], offsets int64
+    [6B+1]): set (pair p, layer l) covers rows offsets[6p+l] .. offsets[6p+l+1] — the ragged layout kpreg_kabsch takes.
+    The random draws differ from the per-pair version (one generator stream for the whole batch)."""
+    dev = coarse_pts.device
+    n_c = coarse_pts.shape[0]
+    n_clouds = coarse_lens.shape[0]
+    n_pairs = n_clouds // 2
+    lens = coarse_lens.to(torch.long)
+    cloud = torch.repeat_interleave(torch.arange(n_clouds, device=dev), lens, output_size=n_c)
+    pair = cloud % n_pairs
+    is_tgt = (cloud >= n_pairs)
+    # group the points of a pair together: sources first, then targets (stable sort keeps their order)
+    perm = torch.argsort(pair, stable=True)
+    pts, pair_s, tgt_s = coarse_pts[perm], pair[perm], is_tgt[perm][:, None]
+    rot, trans = poses[pair_s, :, :3], poses[pair_s, :, 3]
+    fwd = torch.einsum('nij,nj->ni', rot, pts) + trans               # R p + t
+    back = torch.einsum('nji,nj->ni', rot, pts - trans)              # R^T (p - t)
+    a0 = torch.where(tgt_s, back, pts)
+    b0 = torch.where(tgt_s, pts, fwd)
+    n_pair = lens[:n_pairs] + lens[n_pairs:]                          # points per pair
+    cum = torch.nn.functional.pad(torch.cumsum(n_pair, 0), (1, 0))   # [B+1]
+    # flat position f of (pair p, layer l, j): 6 * cum[p] + l * n_p + j
+    f = torch.arange(N_DECODER_LAYERS * n_c, device=dev)
+    p_of_f = torch.searchsorted(N_DECODER_LAYERS * cum[1:], f, right=True)
+    j = (f - N_DECODER_LAYERS * cum[p_of_f]) % n_pair[p_of_f]
+    src_row = cum[p_of_f] + j
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    jitter = noise * torch.randn((2, N_DECODER_LAYERS * n_c, 3), generator=gen, device=dev)
+    t_rows = tgt_s[src_row]
+    a = a0[src_row] + jitter[0] * t_rows
+    b = b0[src_row] + jitter[1] * (~t_rows)
+    w = torch.sigmoid(2.0 * torch.randn(N_DECODER_LAYERS * n_c, generator=gen, device=dev))
+    layer = torch.arange(N_DECODER_LAYERS, device=dev)
+    offsets = (N_DECODER_LAYERS * cum[:-1, None] + layer[None, :] * n_pair[:, None]).reshape(-1)
+    offsets = torch.cat([offsets, (N_DECODER_LAYERS * cum[-1]).reshape(1)]).to(torch.int64)
+    return a.contiguous(), b.contiguous(), w.contiguous(), offsets
+
+
 class RegistrationPath(torch.nn.Module):
     """Preprocessor + KPFEncoder + batched Kabsch behind one call."""
 
@@ -96,12 +139,14 @@ class RegistrationPath(torch.nn.Module):
         feats0 = torch.ones((meta['points'][0].shape[0], 1), dtype=torch.float32, device=meta['points'][0].device)
         feats, _ = self.kpf_encoder(feats0, meta)
         coarse = meta['points'][-1]
-        lens = meta['stack_lengths'][-1].cpu().tolist()
-        a, b, w = synthetic_correspondences(coarse, lens, poses_gt.to(coarse.device), seed=corr_seed)
-        poses = compute_rigid_transform_batch(a, b, w, self.weights_threshold)
-        err = se3_compare(poses[-1], poses_gt.to(coarse.device))
+        poses_dev = poses_gt.to(coarse.device)
+        a, b, w, offsets = synthetic_correspondences_batched(coarse, meta['stack_lengths'][-1], poses_dev, seed=corr_seed)
+        thr = -1.0 if self.weights_threshold is None else float(self.weights_threshold)
+        poses = ops.kabsch(a, b, w, n_pairs * N_DECODER_LAYERS, 0, offsets, thr, False)
+        poses = poses.reshape(n_pairs, N_DECODER_LAYERS, 3, 4).transpose(0, 1).contiguous()   # [6, B, 3, 4]
+        err = se3_compare(poses[-1], poses_dev)
         return {'feats': feats, 'poses': poses, 'rot_deg': err['rot_deg'], 'trans': err['trans'], 'meta': meta,
-                'n_pairs': n_pairs}
+                'n_pairs': n_pairs, 'corr': (a, b, w, offsets)}
 
 
 def result_rows(out: Dict[str, torch.Tensor]) -> torch.Tensor:
