@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
     __syncwarp();
     OutT* row = out + qi * (int64_t)width;
     if (count <= kHitCap) {
-      // rank by counting: keys are distinct (distinct indices), so rank = number of smaller keys
+      // rank by counting: keys are distinct (distinct indices), so rank = number of smaller keys.  (A warp-wide
+      // bitonic sort of the buffer was measured slower: its ~21-28 dependent shared-memory stages are latency-bound,
+      // while these comparisons are independent and pipeline.)
       for (int e = lane; e < count; e += 32) {
         const unsigned long long mine = hits[e];
         int rank = 0;
+#pragma unroll 4
         for (int j = 0; j < count; ++j) rank += (hits[j] < mine) ? 1 : 0;
         if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
       }

@@ -16,27 +16,42 @@ __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, c
   const int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (it >= n_q) return;
   const int64_t n = order ? (int64_t)order[it] : it;  // processing order only
-  for (int c0 = 0; c0 < channels; c0 += 32) {
-    const int c = c0 + lane;
-    float best = -3.402823466e38f;
-    int32_t best_j = (int32_t)n_s;
-    bool any = false;
+  const bool vec = (channels & 3) == 0;  // float4 per lane: 128 channels per pass
+  const int step = vec ? 128 : 32;
+  for (int c0 = 0; c0 < channels; c0 += step) {
+    const int c = c0 + (vec ? 4 * lane : lane);
+    float best[4] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+    int32_t best_j[4] = {(int32_t)n_s, (int32_t)n_s, (int32_t)n_s, (int32_t)n_s};
     for (int h0 = 0; h0 < n_nbrs; h0 += 32) {
       int64_t j = n_s;
       if (h0 + lane < n_nbrs) j = (int64_t)idx[n * n_nbrs + h0 + lane];
       const int lim = min(32, n_nbrs - h0);
+#pragma unroll 4
       for (int hh = 0; hh < lim; ++hh) {
         int64_t jj = __shfl_sync(0xffffffffu, j, hh);
         const bool real = jj >= 0 && jj < n_s;
-        float v = 0.f;
-        if (real && c < channels) v = x[jj * channels + c];
-        if (!real) jj = n_s;
-        if (!any || v > best) { best = v; best_j = (int32_t)jj; any = true; }
+        if (!real) jj = n_s;  // shadow row: zeros
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (real && c < channels) {
+          if (vec) v = *reinterpret_cast<const float4*>(x + jj * channels + c);
+          else v.x = x[jj * channels + c];
+        }
+        // strict > keeps the first maximum, like a sequential scan over the row
+        if (v.x > best[0]) { best[0] = v.x; best_j[0] = (int32_t)jj; }
+        if (v.y > best[1]) { best[1] = v.y; best_j[1] = (int32_t)jj; }
+        if (v.z > best[2]) { best[2] = v.z; best_j[2] = (int32_t)jj; }
+        if (v.w > best[3]) { best[3] = v.w; best_j[3] = (int32_t)jj; }
       }
     }
     if (c < channels) {
-      out[n * channels + c] = any ? best : 0.f;
-      if (argmax) argmax[n * channels + c] = best_j;
+      if (n_nbrs == 0) best[0] = best[1] = best[2] = best[3] = 0.f;
+      if (vec) {
+        *reinterpret_cast<float4*>(out + n * channels + c) = make_float4(best[0], best[1], best[2], best[3]);
+        if (argmax) *reinterpret_cast<int4*>(argmax + n * channels + c) = make_int4(best_j[0], best_j[1], best_j[2], best_j[3]);
+      } else {
+        out[n * channels + c] = best[0];
+        if (argmax) argmax[n * channels + c] = best_j[0];
+      }
     }
   }
 }
