@@ -84,8 +84,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
 
-  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
-    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
+  // each CTA owns a CONTIGUOUS slice of the (spatially sorted) processing order, so the neighbourhoods its warps
+  // gather overlap and stay in this SM's L1
+  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t it = (int64_t)blockIdx.x * per_cta + warp; it < it_end; it += kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only, never the result
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     float acc[CPL][KMAX];
 #pragma unroll
@@ -195,8 +199,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
   const float k1x = k1_ok ? kernel_points[3 * (g + 8)] : 0.f, k1y = k1_ok ? kernel_points[3 * (g + 8) + 1] : 0.f,
               k1z = k1_ok ? kernel_points[3 * (g + 8) + 2] : 0.f;
 
-  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
-    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
+  // each CTA owns a CONTIGUOUS slice of the (spatially sorted) processing order, so the neighbourhoods its warps
+  // gather overlap and stay in this SM's L1
+  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t it = (int64_t)blockIdx.x * per_cta + warp; it < it_end; it += kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only, never the result
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     // neighbours h = lane and h = lane + 32: index and relative position, fetched once, shuffled per k-step
     int64_t jn[2];
@@ -301,8 +309,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
   __syncthreads();
-  for (int64_t it = (int64_t)blockIdx.x * kGatherWarps + warp; it < n_q; it += (int64_t)gridDim.x * kGatherWarps) {
-    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only (spatially sorted -> L1 reuse)
+  // each CTA owns a CONTIGUOUS slice of the (spatially sorted) processing order, so the neighbourhoods its warps
+  // gather overlap and stay in this SM's L1
+  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t it = (int64_t)blockIdx.x * per_cta + warp; it < it_end; it += kGatherWarps) {
+    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only, never the result
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
     float da[CPL][KMAX];
     const float* __restrict__ drow = d_agg + n * (int64_t)n_kpts * c_in;

@@ -35,7 +35,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;          // floats per 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32
-constexpr int kGemmThreads = 320;
+constexpr int gemm_threads(int block_n) { return 64 + 128 + 32 * (block_n >= 64 ? 8 : 4); }  // TMA, MMA, 4 splitters, 4|8 epilogue warps
 constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -113,8 +113,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = hi + lo with hi = x rounded to nearest TF32 and lo = (x - hi) rounded to nearest TF32 (x - hi is exact in
 // fp32); both are exactly representable, so the tensor core's own fp32->tf32 conversion changes nothing.
@@ -140,6 +140,7 @@ struct Epilogue {
   const float* addend;     // [M, ld_add]
   int ld2, ld_add;
   int vec_ok;              // every row pointer (C, residual, out2, addend) is 16-byte aligned: float4 accesses allowed
+  int col_vec;             // col_scale / col_shift are 16-byte aligned: float4 broadcast loads allowed
   int tma_store;           // C (and out2) leave through TMA stores from a swizzled shared-memory tile (needs vec_ok)
 };
 
@@ -150,8 +151,9 @@ struct SmemLayout {
   static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
   static constexpr uint32_t kStageBytes = 2 * kABoxBytes + 2 * kBBoxBytes;
   static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
-  static constexpr uint32_t kStoreBytes = 4 * 4096;           // per epilogue warp: one 32 x 32 fp32 tile for TMA stores
-  static constexpr uint32_t kEpiBytes = kStoreBytes + 4 * 2 * BLOCK_N * 4;  // + per warp column scale / shift of the tile
+  static constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;      // two warps per TMEM lane quarter share a tile's 32-column chunks
+  static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;   // per epilogue warp: one 32 x 32 fp32 tile for TMA stores
+  static constexpr uint32_t kEpiBytes = kStoreBytes;
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
   static constexpr uint32_t kTmemCols = 2 * kNumAcc * BLOCK_N;  // double-buffered accumulators
@@ -168,7 +170,7 @@ struct SmemLayout {
 // (2^-11 smaller) cross terms therefore get their own accumulator, and for long K the hi*hi products of
 // consecutive k-steps rotate over three accumulators; the epilogue adds them in fp32 round-to-nearest.
 template <int BLOCK_N, int NUM_HI, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo,
                                                           const __grid_constant__ CUtensorMap map_c,
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), 4);
+      mbar_init(tmem_empty_bar(b), L::kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -294,14 +296,17 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
       }
     }
   } else {
-    // ---------------- epilogue (warps 6..9): warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row
+    // ---------------- epilogue (warps 6..): warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row.  With
+    // 8 epilogue warps, the two warps of a lane quarter take alternate 32-column chunks of the tile.
     const int q = warp & 3;
-    float* s_cs = reinterpret_cast<float*>(base_ptr + L::kTileBytes + L::kStoreBytes) + q * (2 * BLOCK_N);
-    float* s_cb = s_cs + BLOCK_N;
-    uint8_t* stg_ptr = base_ptr + L::kTileBytes + q * 4096;  // 1024-byte aligned (SWIZZLE_128B)
-    const uint32_t stg = base + L::kTileBytes + (uint32_t)q * 4096u;
+    const int ew = warp - 6;                       // 0 .. kEpiWarps-1
+    const int half = ew >> 2;                      // which chunk parity this warp handles
+    constexpr int kChunkStep = 32 * (L::kEpiWarps / 4);
+    uint8_t* stg_ptr = base_ptr + L::kTileBytes + ew * 4096;  // 1024-byte aligned (SWIZZLE_128B)
+    const uint32_t stg = base + L::kTileBytes + (uint32_t)ew * 4096u;
     const bool vec_ok = ep.vec_ok != 0;
     const bool tma_out = ep.tma_store != 0;
+    const bool col_vec = ep.col_vec != 0;
     if (tma_out && lane == 0) {
       tma_prefetch_desc(&map_c);
       if (ep.out2) tma_prefetch_desc(&map_o2);
@@ -311,14 +316,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
       const int64_t m = (tile / num_n) * BLOCK_M + 32 * q + lane;
       const int n0 = (int)(tile % num_n) * BLOCK_N;
       const uint32_t buf = lt & 1u;
-      // column parameters of this tile -> this warp's shared slice (read back as broadcasts)
-      for (int j = lane; j < BLOCK_N; j += 32) {
-        const int n = n0 + j;
-        s_cs[j] = (ep.col_scale && n < N) ? ep.col_scale[n] : 1.0f;
-        s_cb[j] = (ep.col_shift && n < N) ? ep.col_shift[n] : 0.0f;
-      }
       const float rs = (ep.row_scale && m < M) ? ep.row_scale[m] : 1.0f;
-      __syncwarp();
       mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1u);
       tcgen05_fence_after();
       const uint32_t acc0 = tmem_base + buf * (kNumAcc * BLOCK_N) + ((uint32_t)(32 * q) << 16);
@@ -327,22 +325,51 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
       float* __restrict__ orow = ep.out2 ? ep.out2 + m * (int64_t)ep.ld2 : nullptr;
       const float* __restrict__ arow = ep.out2 ? ep.addend + m * (int64_t)ep.ld_add : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 32 * half; c0 < BLOCK_N; c0 += kChunkStep) {
         float sum[32];
         {
-          uint32_t r[32];
+          // the accumulators of this chunk: issue the TMEM loads pairwise, one wait per pair
+          uint32_t r[32], r2[32];
           tmem_ld_32x32b_x32(acc0 + (uint32_t)c0, r);
+          tmem_ld_32x32b_x32(acc0 + (uint32_t)(BLOCK_N + c0), r2);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+          if constexpr (kNumAcc == 4) {
+            tmem_ld_32x32b_x32(acc0 + (uint32_t)(2 * BLOCK_N + c0), r);
+            tmem_ld_32x32b_x32(acc0 + (uint32_t)(3 * BLOCK_N + c0), r2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int a = 1; a < kNumAcc; ++a) {
-            tmem_ld_32x32b_x32(acc0 + (uint32_t)(a * BLOCK_N + c0), r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
           }
         }
-        if (c0 + 32 >= BLOCK_N) {
-          // all TMEM reads of this tile are done: hand the accumulator set back to the MMA warp
+        // row scale, column scale / shift (same addresses in every lane: broadcast loads, L1 resident)
+        if (ep.row_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] *= rs;
+        }
+        if (ep.col_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (col_vec && n + 3 < N) s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + n));
+            else { if (n < N) s4.x = ep.col_scale[n]; if (n + 1 < N) s4.y = ep.col_scale[n + 1]; if (n + 2 < N) s4.z = ep.col_scale[n + 2]; if (n + 3 < N) s4.w = ep.col_scale[n + 3]; }
+            sum[j] *= s4.x; sum[j + 1] *= s4.y; sum[j + 2] *= s4.z; sum[j + 3] *= s4.w;
+          }
+        }
+        if (ep.col_shift) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_vec && n + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(ep.col_shift + n));
+            else { if (n < N) b4.x = ep.col_shift[n]; if (n + 1 < N) b4.y = ep.col_shift[n + 1]; if (n + 2 < N) b4.z = ep.col_shift[n + 2]; if (n + 3 < N) b4.w = ep.col_shift[n + 3]; }
+            sum[j] += b4.x; sum[j + 1] += b4.y; sum[j + 2] += b4.z; sum[j + 3] += b4.w;
+          }
+        }
+        if (c0 + kChunkStep >= BLOCK_N) {
+          // this warp's TMEM reads of the tile are done: hand the accumulator set back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
@@ -357,7 +384,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
             const int n = n0 + c0 + j;
             float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = sum[j + e] * rs * s_cs[c0 + j + e] + s_cb[c0 + j + e];
+            for (int e = 0; e < 4; ++e) v[e] = sum[j + e];
             const bool in4 = (m < M) && (n + 3 < N);
             if (rrow) {
               if (in4) {
@@ -410,7 +437,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tc(const __grid_constant_
             const bool full4 = vec_ok && (n + 3 < N);
             float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = sum[j + e] * rs * s_cs[c0 + j + e] + s_cb[c0 + j + e];
+            for (int e = 0; e < 4; ++e) v[e] = sum[j + e];
             if (rrow) {
               if (full4) {
                 const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
@@ -519,7 +546,7 @@ int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUte
   }
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, kGemmThreads, L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -578,7 +605,8 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   if (rc) return rc;
   rc = make_map(&mo2, (tma_store && out2) ? out2 : nullptr, m, n, ld2, 32);
   if (rc) return rc;
-  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, tma_store};
+  const int col_vec = ((reinterpret_cast<uintptr_t>(col_scale) | reinterpret_cast<uintptr_t>(col_shift)) & 15) == 0;
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, col_vec, tma_store};
   if (num_hi == 3) {
     if (block_n == 32) return launch_tile_config<32, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     return launch_tile_config<64, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);

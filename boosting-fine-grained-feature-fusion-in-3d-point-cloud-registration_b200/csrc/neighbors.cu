@@ -222,8 +222,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
   int my_max = 0;
   unsigned long long* hits = s_hits[warp];
 
-  for (int64_t it = (int64_t)blockIdx.x * kWarpsPerBlock + warp; it < n_queries; it += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t qi = order ? (int64_t)order[it] : it;  // processing order only (cell-sorted queries share cells)
+  // each CTA owns a contiguous slice of the (cell-sorted) processing order: its queries share cells -> L1 hits
+  const int64_t per_cta = (n_queries + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_queries, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t it = (int64_t)blockIdx.x * per_cta + warp; it < it_end; it += kWarpsPerBlock) {
+    const int64_t qi = order ? (int64_t)order[it] : it;  // processing order only, never the result
     const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
     const int cloud = cloud_of(q_off, n_clouds, qi);
     const int64_t cloud_base = s_off[cloud];
