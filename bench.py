@@ -331,7 +331,8 @@ def main():
 
     # clock / allocator / page-cache ramp-up of a fresh box: run the step untimed for ~2 s before the W warm-up steps
     t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 2.0:
+    ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
+    while time.perf_counter() - t_ramp < ramp_s:
         step_resident()
         torch.cuda.synchronize()
 

@@ -91,3 +91,16 @@ def test_shard_pairs_round_robin():
     shards = [shard_pairs(10, r, 4) for r in range(4)]
     assert shards == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
     assert sorted(sum(shards, [])) == list(range(10))
+
+
+def test_compute_overlaps_matches_reference_formula():
+    """compute_overlaps (reference finegrained_kpconv.py:545-571) on a hand-made 2-level pyramid."""
+    from kpreg_b200.kpconv import PreprocessorGPU, Preprocessor, compute_overlaps
+    assert PreprocessorGPU is Preprocessor
+    pools0 = torch.tensor([[0, 1, 5], [2, 5, 5], [3, 4, 0]])           # 5 = pad (level 0 has 5 points)
+    batch = {'src_overlap': [torch.tensor([True, False, True])], 'tgt_overlap': [torch.tensor([False, True])],
+             'kpconv_meta': {'points': [torch.zeros(5, 3), torch.zeros(3, 3)], 'pools': [pools0, torch.zeros(0, 1)],
+                             'stack_lengths': [torch.tensor([3, 2]), torch.tensor([2, 1])]}}
+    out = compute_overlaps(batch)
+    assert torch.equal(out['pyr_0'], torch.tensor([1., 0., 1., 0., 1.]))
+    assert torch.allclose(out['pyr_1'], torch.tensor([0.5, 1.0, (0. + 1. + 1.) / 3]))
