@@ -378,6 +378,18 @@ def main():
             "grid_query_GBs": work["query_bytes"] / max(fam_ms["grid_query"], 1e-9) / 1e6,
             "segment_norm_GBs": work["segment_norm_bytes"] / max(fam_ms["segment_norm"], 1e-9) / 1e6,
         }
+        # DRAM traffic of the family from the committed ncu capture (profiles/r1d_dram_traffic.json: dram__bytes_read.sum +
+        # dram__bytes_write.sum over one step's launches at 8 pairs), scaled to this run's pairs per step
+        tpath = os.path.join(ROOT, "profiles", "r1d_dram_traffic.json")
+        fam_kernel = {"linear": "k_gemm_tc", "kpconv_contract": "k_gemm_tc", "kpconv_gather": "k_kpconv_gather_mma",
+                      "grid_query": "k_grid_query"}.get(top)
+        if os.path.exists(tpath) and fam_kernel:
+            tr = json.load(open(tpath))
+            f = tr["families"].get(fam_kernel)
+            if f:
+                roof["traffic"] = (f["dram_read_MB"] + f["dram_write_MB"]) * 1e6 * args.pairs / tr["pairs"]
+                roof["traffic_note"] = (f"bytes per step, all {fam_kernel} launches (ncu capture at {tr['pairs']} pairs/step scaled to "
+                                        f"{args.pairs}); achieved / algorithmic figures are per step as well")
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
