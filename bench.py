@@ -333,7 +333,8 @@ def main():
     t_ramp = time.perf_counter()
     ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
     while time.perf_counter() - t_ramp < ramp_s:
-        step_resident()
+        # local work only: the iteration count is time-based and differs per rank, so NO collective in here
+        path(src_dev, tgt_dev, poses_dev)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
