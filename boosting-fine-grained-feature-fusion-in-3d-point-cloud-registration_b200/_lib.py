@@ -97,7 +97,13 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (the raw getter avoids building a Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -130,8 +136,7 @@ class _Workspaces:
         self._bufs: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(),
-               torch.cuda.current_stream(device).cuda_stream)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             # keep the old buffer alive until queued kernels are done: record it on the stream
@@ -145,7 +150,17 @@ class _Workspaces:
 workspaces = _Workspaces()
 
 
+_SIZE_CACHE: Dict[tuple, int] = {}
+
+
 def size_query(fn_name: str, *args) -> int:
-    out = _c_size(0)
-    check(getattr(load(), fn_name)(*args, ctypes.byref(out)), fn_name)
-    return int(out.value)
+    """Workspace size from a kpreg_*_workspace_bytes entry point (pure functions of their arguments: memoised)."""
+    key = (fn_name,) + args
+    hit = _SIZE_CACHE.get(key)
+    if hit is None:
+        out = _c_size(0)
+        check(getattr(load(), fn_name)(*args, ctypes.byref(out)), fn_name)
+        hit = int(out.value)
+        if len(_SIZE_CACHE) < 65536:
+            _SIZE_CACHE[key] = hit
+    return hit

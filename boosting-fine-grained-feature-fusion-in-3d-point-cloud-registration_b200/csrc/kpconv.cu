@@ -282,16 +282,22 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
     }
     // D fragment: rows (kernel points) g and g + 8, columns (channels) 8 i + 2 t, + 1
     float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in;
+    const bool pair_ok = (c_in & 1) == 0;  // (row * c_in + even column) is then 8-byte aligned: one float2 store
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int c = 8 * i + 2 * t;
-      if (k0_ok) {
-        if (c < c_in) arow[g * c_in + c] = acc[i][0];
-        if (c + 1 < c_in) arow[g * c_in + c + 1] = acc[i][1];
-      }
-      if (k1_ok) {
-        if (c < c_in) arow[(g + 8) * c_in + c] = acc[i][2];
-        if (c + 1 < c_in) arow[(g + 8) * c_in + c + 1] = acc[i][3];
+      if (pair_ok && c + 1 < c_in) {
+        if (k0_ok) *reinterpret_cast<float2*>(arow + g * c_in + c) = make_float2(acc[i][0], acc[i][1]);
+        if (k1_ok) *reinterpret_cast<float2*>(arow + (g + 8) * c_in + c) = make_float2(acc[i][2], acc[i][3]);
+      } else {
+        if (k0_ok) {
+          if (c < c_in) arow[g * c_in + c] = acc[i][0];
+          if (c + 1 < c_in) arow[g * c_in + c + 1] = acc[i][1];
+        }
+        if (k1_ok) {
+          if (c < c_in) arow[(g + 8) * c_in + c] = acc[i][2];
+          if (c + 1 < c_in) arow[(g + 8) * c_in + c + 1] = acc[i][3];
+        }
       }
     }
     if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);

@@ -223,6 +223,43 @@ def compute_overlaps(batch):
     return pyramid
 
 
+def calibrate_neighbors(dataset, config, collate_fn=None, keep_ratio=0.8, samples_threshold=2000):
+    """Neighbourhood limits for a dataset (reference :707-739): histogram the per-point neighbour counts of every
+    pyramid level over the dataset (until each level has more than ``samples_threshold`` samples) and keep, per level,
+    the count below which ``keep_ratio`` of the points fall.  The pyramids are built on the device with the row limit
+    lifted to the reference's bound ceil(4/3 pi (deform_radius + 1)^3).
+
+    ``dataset[i]`` is a pair in collate_pair's format ({'src_xyz': [N,3], 'tgt_xyz': [M,3]}), a (src, tgt) tuple or
+    a single [N,3] cloud; ``collate_fn`` (optional) maps an item to a list of [N,3] tensors instead."""
+    from .config import AttrDict
+    hist_n = int(np.ceil(4 / 3 * np.pi * (config.deform_radius + 1) ** 3))
+    n_layers = int(config.num_layers)
+    wide = AttrDict(dict(config))
+    wide['neighborhood_limits'] = [hist_n] * max(n_layers, len(config.neighborhood_limits))
+    pre = Preprocessor(wide, index_dtype=torch.int32)
+    hists = torch.zeros((n_layers, hist_n), dtype=torch.int64)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    for i in range(len(dataset)):
+        item = dataset[i]
+        if collate_fn is not None:
+            clouds = collate_fn(item)
+        elif isinstance(item, dict):
+            clouds = [item['src_xyz'], item['tgt_xyz']]
+        elif isinstance(item, (tuple, list)):
+            clouds = list(item[:2])
+        else:
+            clouds = [item]
+        clouds = [torch.as_tensor(c, dtype=torch.float32).to(dev) for c in clouds]
+        meta = pre(clouds)
+        for lvl, table in enumerate(meta['neighbors'][:n_layers]):
+            counts = (table < table.shape[0]).sum(dim=1)
+            hists[lvl] += torch.bincount(counts, minlength=hist_n)[:hist_n].cpu()
+        if int(hists.sum(dim=1).min()) > samples_threshold:
+            break
+    cumsum = torch.cumsum(hists.t(), dim=0)
+    return (cumsum < keep_ratio * cumsum[hist_n - 1, :].to(torch.float64)).sum(dim=0).numpy()
+
+
 class KPFEncoder(torch.nn.Module):
     def __init__(self, config, d_bottle, increase_channel_when_downsample=True):
         super().__init__()

@@ -304,7 +304,9 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     x, ldx = _rows(x, "x")
     m, k = x.shape
     presplit = None
-    if gemm == 1 and not torch.is_grad_enabled() and lib.kpreg_gemm_supported(m, k, int(weight.shape[0]), ldx, x.data_ptr()):
+    # the TMA path's addressing rule (kpreg_gemm_supported): K >= 4, N >= 8, 16-byte aligned base and row pitch
+    if (gemm == 1 and not torch.is_grad_enabled() and m > 0 and k >= 4 and weight.shape[0] >= 8 and ldx % 4 == 0
+            and x.data_ptr() % 16 == 0):
         presplit = cached_split(weight, False)  # inference: the weights were split once
     weight = _f32c(weight, "weight")
     n = weight.shape[0]

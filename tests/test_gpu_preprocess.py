@@ -190,3 +190,22 @@ def test_pyramid_mcd_shape_sparse_grid(oracle):
     want = oracle.preprocess([src, tgt], cfg, impl=_impl(oracle))
     meta = Preprocessor(cfg)([cuda(src), cuda(tgt)])
     check_pyramid(oracle, meta_to_numpy(meta), want, cfg)
+
+
+def test_calibrate_neighbors_matches_reference_procedure(oracle):
+    """calibrate_neighbors (reference finegrained_kpconv.py:707-739) on a small synthetic dataset vs the same
+    histogram / percentile procedure over the CPU oracle's tables."""
+    from kpreg_b200.kpconv import calibrate_neighbors
+    cfg = kpconv_config("modelnet")
+    data = [dict(zip(("src_xyz", "tgt_xyz"), synthetic.modelnet_pair(seed=50 + i)[:2])) for i in range(3)]
+    got = calibrate_neighbors(data, cfg, keep_ratio=0.8, samples_threshold=10 ** 9)
+    hist_n = int(np.ceil(4 / 3 * np.pi * (cfg.deform_radius + 1) ** 3))
+    wide = kpconv_config("modelnet", neighborhood_limits=[hist_n] * 2)
+    hists = np.zeros((cfg.num_layers, hist_n), np.int64)
+    for item in data:
+        meta = oracle.preprocess([item["src_xyz"], item["tgt_xyz"]], wide, impl=_impl(oracle))
+        for lvl, t in enumerate(meta["neighbors"][:cfg.num_layers]):
+            hists[lvl] += np.bincount((t < t.shape[0]).sum(1), minlength=hist_n)[:hist_n]
+    cumsum = np.cumsum(hists.T, axis=0)
+    want = np.sum(cumsum < (0.8 * cumsum[hist_n - 1, :]), axis=0)
+    assert np.array_equal(got, want)
