@@ -469,7 +469,7 @@ int launch_gemm(const float* A, const float* B, float* C, const float* row_scale
 }
 
 struct KpconvWs {
-  unsigned char* row_pos; float* inv_num; float* agg; float* d_agg; float* g_scaled; float* w_split; void* gemm_ws; size_t total;
+  unsigned char* row_pos; float* inv_num; float* agg; float* d_agg; float* g_scaled; float* w_split; size_t total;
 };
 
 KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out, int backward) {
@@ -486,7 +486,6 @@ KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in
     w.g_scaled = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * (size_t)c_out);
   }
   w.w_split = reinterpret_cast<float*>(cv.take<char>(kpconv_gemm_tc_weight_bytes((int)kd, c_out)));
-  w.gemm_ws = cv.take<char>(4096);
   w.total = align_up(cv.used, 256);
   return w;
 }

@@ -16,8 +16,8 @@
 // Query (one warp per query point):
 //   lanes 0..26 look up the 27 surrounding cells; the warp then walks the concatenated ranges 32
 //   candidates at a time (coalesced 16-byte loads), compacts the hits with a ballot into shared
-//   memory as 64-bit (d2 bits << 32 | index) keys, ranks them by counting and writes the row with
-//   coalesced (vectorised when the width allows) stores.
+//   memory as 64-bit (d2 bits << 32 | index) keys, ranks them by counting and writes each index at its rank
+//   (a row is one contiguous 4*width-byte span, so the scattered 4-byte stores of a warp fall into 1-2 lines).
 #include <cub/cub.cuh>
 
 #include "common.cuh"
