@@ -49,7 +49,8 @@ def test_tc_contraction_many_row_tiles(oracle):
     assert rel_err(simt.cpu().numpy(), want.numpy()) < 1e-4
 
 
-@pytest.mark.parametrize("m,k,n", [(5000, 32, 128), (1000, 28, 28), (777, 224, 224), (4096, 128, 32), (130, 1024, 256), (300, 3, 16)])
+@pytest.mark.parametrize("m,k,n", [(5000, 32, 128), (1000, 28, 28), (777, 224, 224), (4096, 128, 32), (130, 1024, 256), (300, 3, 16),
+                                   (513, 40, 30), (64, 96, 72), (2000, 1100, 40)])
 @pytest.mark.parametrize("gemm", [1, 0])
 def test_linear_forward_matches_torch(m, k, n, gemm):
     """nn.Linear(bias=False) + folded BatchNorm + residual + activation (+ the chained second output)."""
