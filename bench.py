@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm", type=int, default=None, help="contractions: 0 fp32 CUDA cores, 1 tcgen05 3xTF32 (default)")
     ap.add_argument("--no-fused-glue", action="store_true", help="run the block glue on stock PyTorch ops")
