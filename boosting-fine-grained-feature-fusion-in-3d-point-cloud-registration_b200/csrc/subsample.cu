@@ -15,7 +15,7 @@
 //   6. segmented mean                     k_voxels: one thread per voxel adds its points
 //      sequentially in input order (fp32, like SampledData::update_points, grid_subsampling.h:74-79)
 //      and scales by (float)(1.0/count) (reference :87)
-//   7. hash-table order                   k_order: one CTA per cloud replays the table's growth
+//   7. hash-table order                   k_order: one CTA (or, for large clouds, one 8-CTA cluster) per cloud replays the table's growth
 //      13 -> 29 -> 59 -> ... (libstdc++ prime policy, load factor 1) as ~log2(m) parallel rounds.
 //      For a fixed bucket count the list order is a pure function of the insertion sequence S:
 //      buckets by descending first appearance in S, inside a bucket by descending position in S;
@@ -225,22 +225,27 @@ __device__ __forceinline__ int block_scan_inclusive(int v, int* smem_warp, int& 
   return incl + prev;
 }
 
-// One CTA per cloud: replay the unordered_map's list order.  Scratch arrays are per point/cloud:
+// Replay of the unordered_map's list order: one TEAM per cloud — a single CTA, or for large clouds a thread-block
+// cluster of CS CTAs that synchronise with barrier.cluster between the passes of a growth round (the early rounds,
+// whose tables are tiny, are run by the cluster's first CTA alone).  Scratch arrays are per point/cloud:
 //   list0/list1/nxt/start/bkt : capacity len_c, at offset off[c]
 //   b_first/b_count/b_head    : capacity 3*len_c + 16, at offset 3*off[c] + 16*c
-template <int THREADS>
+//   part                      : 16 ints per cloud (per-CTA scan totals of a cluster)
+constexpr unsigned int kSoloTable = 5087;  // growth rounds up to this table size stay on one CTA
+
+template <int THREADS, int CS>
 __global__ void __launch_bounds__(THREADS) k_order(
     const int64_t* __restrict__ off, const int64_t* __restrict__ voff, const uint64_t* __restrict__ vkey,
     const float* __restrict__ bary, const int64_t* __restrict__ ooff, const int32_t* __restrict__ out_counts,
     int32_t* __restrict__ list0, int32_t* __restrict__ list1, int32_t* __restrict__ nxt, int32_t* __restrict__ start,
     uint32_t* __restrict__ bkt, int32_t* __restrict__ b_first, int32_t* __restrict__ b_count,
-    int32_t* __restrict__ b_head, float* __restrict__ out_pts) {
+    int32_t* __restrict__ b_head, int32_t* __restrict__ part_all, float* __restrict__ out_pts) {
   __shared__ int s_warp[32];
-  const int c = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int c = blockIdx.x / CS;
+  const int rank = blockIdx.x % CS;  // == %cluster_ctarank for a 1-D cluster of CS CTAs
   const int64_t vbase = voff[c];
   const int m = (int)(voff[c + 1] - vbase);
-  if (m == 0) return;
+  if (m == 0) return;  // uniform over the cluster
   const int64_t pbase = off[c];
   const int64_t bbase = 3 * pbase + 16 * (int64_t)c;
   int32_t* cur = list0 + pbase;
@@ -251,59 +256,96 @@ __global__ void __launch_bounds__(THREADS) k_order(
   int32_t* bF = b_first + bbase;
   int32_t* bC = b_count + bbase;
   int32_t* bH = b_head + bbase;
+  int32_t* part = part_all + 16 * (int64_t)c;
   const uint64_t* key = vkey + vbase;
 
+  auto cluster_sync = [&]() {
+    if constexpr (CS > 1) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      __syncthreads();
+    }
+  };
+
   int n_prev = 0;
+  bool team_mode = false;  // false: this round is run by CTA 0 of the cluster alone
   for (int g = 0;; ++g) {
     const unsigned int nb = c_table_sizes[g];
     const int n = (unsigned int)m < nb ? m : (int)nb;
-    for (unsigned int b = tid; b < nb; b += THREADS) {
-      bF[b] = 0x7fffffff;
-      bC[b] = 0;
-      bH[b] = -1;
+    if (CS > 1 && !team_mode && nb > kSoloTable) {
+      cluster_sync();  // hand-over: CTA 0's lists become visible to the whole cluster
+      team_mode = true;
     }
-    __syncthreads();
-    // insertion sequence S: the previous list front to back, then the new voxels by first appearance
-    for (int pos = tid; pos < n; pos += THREADS) {
-      const int r = pos < n_prev ? cur[pos] : pos;
-      const unsigned int b = (unsigned int)(key[r] % (uint64_t)nb);
-      bk[pos] = b;
-      atomicMin(&bF[b], pos);
-      atomicAdd(&bC[b], 1);
-      chain[pos] = atomicExch(&bH[b], pos);
-    }
-    __syncthreads();
-    // start[pos] for bucket-first positions = number of elements in buckets that appear later in S
-    int carry = 0;
-    for (int t0 = 0; t0 < n; t0 += THREADS) {
-      const int rpos = t0 + tid;
-      const int pos = n - 1 - rpos;
-      int v = 0;
-      if (rpos < n) {
-        const unsigned int b = bk[pos];
-        v = (bF[b] == pos) ? bC[b] : 0;
+    const int team = team_mode ? CS : 1;
+    const bool active = team_mode || rank == 0;
+    const int tid = (team_mode ? rank : 0) * THREADS + (int)threadIdx.x;
+    const int nthreads = team * THREADS;
+    auto team_sync = [&]() { if (team_mode) cluster_sync(); else __syncthreads(); };
+
+    if (active) {
+      for (unsigned int b = tid; b < nb; b += nthreads) {
+        bF[b] = 0x7fffffff;
+        bC[b] = 0;
+        bH[b] = -1;
       }
-      int total;
-      const int incl = block_scan_inclusive<THREADS>(v, s_warp, total);
-      if (rpos < n) st[pos] = carry + incl - v;
-      carry += total;
+      team_sync();
+      // insertion sequence S: the previous list front to back, then the new voxels by first appearance
+      for (int pos = tid; pos < n; pos += nthreads) {
+        const int r = pos < n_prev ? cur[pos] : pos;
+        const unsigned int b = (unsigned int)(key[r] % (uint64_t)nb);
+        bk[pos] = b;
+        atomicMin(&bF[b], pos);
+        atomicAdd(&bC[b], 1);
+        chain[pos] = atomicExch(&bH[b], pos);
+      }
+      team_sync();
+      // start[pos] for bucket-first positions = number of elements in buckets that appear later in S: an exclusive
+      // scan over the REVERSED positions; every CTA of the team scans one contiguous chunk, then adds the totals of
+      // the chunks before it
+      const int chunk = (n + team - 1) / team;
+      const int lo = (team_mode ? rank : 0) * chunk;
+      const int hi = min(n, lo + chunk);
+      int carry = 0;
+      for (int t0 = lo; t0 < hi; t0 += THREADS) {
+        const int rpos = t0 + (int)threadIdx.x;
+        const int pos = n - 1 - rpos;
+        int v = 0;
+        if (rpos < hi) {
+          const unsigned int b = bk[pos];
+          v = (bF[b] == pos) ? bC[b] : 0;
+        }
+        int total;
+        const int incl = block_scan_inclusive<THREADS>(v, s_warp, total);
+        if (rpos < hi) st[pos] = carry + incl - v;
+        carry += total;
+      }
+      if (team_mode) {
+        if (threadIdx.x == 0) part[rank] = carry;
+        cluster_sync();
+        int before = 0;
+        for (int r = 0; r < rank; ++r) before += part[r];
+        if (before != 0)
+          for (int rpos = lo + (int)threadIdx.x; rpos < hi; rpos += THREADS) st[n - 1 - rpos] += before;
+      }
+      team_sync();
+      for (int pos = tid; pos < n; pos += nthreads) {
+        const int r = pos < n_prev ? cur[pos] : pos;
+        const unsigned int b = bk[pos];
+        int later = 0;
+        for (int j = bH[b]; j != -1; j = chain[j]) later += (j > pos) ? 1 : 0;
+        nxl[st[bF[b]] + later] = r;
+      }
+      team_sync();
     }
-    __syncthreads();
-    for (int pos = tid; pos < n; pos += THREADS) {
-      const int r = pos < n_prev ? cur[pos] : pos;
-      const unsigned int b = bk[pos];
-      int later = 0;
-      for (int j = bH[b]; j != -1; j = chain[j]) later += (j > pos) ? 1 : 0;
-      nxl[st[bF[b]] + later] = r;
-    }
-    __syncthreads();
     int32_t* t = cur; cur = nxl; nxl = t;
     n_prev = n;
     if (n == m) break;
   }
+  if (CS > 1 && !team_mode) cluster_sync();  // small cloud finished by CTA 0 alone: publish its list to the cluster
   const int keep = out_counts[c];
   const int64_t obase = ooff[c];
-  for (int j = tid; j < keep; j += THREADS) {
+  for (int j = rank * THREADS + (int)threadIdx.x; j < keep; j += CS * THREADS) {
     const int64_t v = vbase + cur[j];
     out_pts[3 * (obase + j) + 0] = bary[3 * v + 0];
     out_pts[3 * (obase + j) + 1] = bary[3 * v + 1];
@@ -316,7 +358,7 @@ struct SubsampleWs {
   uint64_t* keys0; uint64_t* keys1; uint32_t* idx0; uint32_t* idx1;
   uint32_t* first_flag; uint32_t* rank; float* bary; uint64_t* vkey;
   int32_t* list0; int32_t* list1; int32_t* nxt; int32_t* start; uint32_t* bkt;
-  int32_t* b_first; int32_t* b_count; int32_t* b_head;
+  int32_t* b_first; int32_t* b_count; int32_t* b_head; int32_t* part;
   void* cub_tmp; size_t cub_tmp_bytes; size_t total;
 };
 
@@ -348,6 +390,7 @@ SubsampleWs carve_subsample(void* base, int64_t n, int n_clouds) {
   w.b_first = cv.take<int32_t>(nbk);
   w.b_count = cv.take<int32_t>(nbk);
   w.b_head = cv.take<int32_t>(nbk);
+  w.part = cv.take<int32_t>(16 * nc + 16);
   w.cub_tmp_bytes = (size_t)(8u << 20) + np * 16;
   w.cub_tmp = cv.take<char>(w.cub_tmp_bytes);
   w.total = align_up(cv.used, 256);
@@ -422,8 +465,29 @@ extern "C" int kpreg_subsample_batch(const float* pts, const int32_t* lens, int6
   KP_LAUNCH_CHECK();
   k_voxels<<<pt_blocks, 256, 0, stream>>>(pts, ks, is, w.rank, n, w.bary, w.vkey);
   KP_LAUNCH_CHECK();
-  k_order<1024><<<n_clouds, 1024, 0, stream>>>(w.off, w.voff, w.vkey, w.bary, w.ooff, out_counts, w.list0, w.list1,
-                                              w.nxt, w.start, w.bkt, w.b_first, w.b_count, w.b_head, out_pts);
+  if (n / n_clouds > 32768) {
+    // large clouds: a cluster of 8 CTAs per cloud (the rounds of the replay are parallel over the cloud's voxels)
+    constexpr int kCluster = 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clouds * kCluster));
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KP_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_order<1024, kCluster>, (const int64_t*)w.off, (const int64_t*)w.voff,
+                                   (const uint64_t*)w.vkey, (const float*)w.bary, (const int64_t*)w.ooff,
+                                   (const int32_t*)out_counts, w.list0, w.list1, w.nxt, w.start, w.bkt, w.b_first, w.b_count,
+                                   w.b_head, w.part, out_pts));
+  } else {
+    k_order<1024, 1><<<n_clouds, 1024, 0, stream>>>(w.off, w.voff, w.vkey, w.bary, w.ooff, out_counts, w.list0, w.list1,
+                                                   w.nxt, w.start, w.bkt, w.b_first, w.b_count, w.b_head, w.part, out_pts);
+  }
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }

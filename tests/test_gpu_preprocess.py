@@ -21,7 +21,7 @@ def _impl(oracle):
 @pytest.mark.parametrize("seed,lens,dl", [
     (0, [1], 0.1), (1, [13, 14, 15], 0.05), (2, [29, 30, 1, 2], 0.02), (3, [500, 257, 258], 0.07),
     (4, [6000, 3000], 0.04), (5, [6000, 100], 5.0), (6, [30000, 20000, 10000], 0.03), (7, [5] * 40, 0.3),
-    (8, [120000], 0.021)])
+    (8, [120000], 0.021), (9, [100000, 5, 70000, 1], 0.03), (10, [40000, 300000], 0.012)])
 def test_subsample_bit_exact(oracle, seed, lens, dl):
     rng = np.random.default_rng(seed)
     lens = np.array(lens, np.int32)
