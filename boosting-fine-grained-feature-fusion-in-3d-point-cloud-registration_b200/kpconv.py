@@ -158,15 +158,10 @@ class Preprocessor(nn.Module):
             layer_blocks = []
 
         if pending_up is not None:
-            # architecture ended on a strided block: the upsample table still needs the coarse grid
+            # the architecture ended on a strided block: its upsample table is answered by the grid already built over
+            # the pooled points; like the reference, no further level is appended (finegrained_kpconv.py:395-409)
             up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3], pending_up[4]))
             pending_up = None
-            level_points.append(points)
-            level_lens.append(lens)
-            level_orders.append(grid.order if grid is not None else None)
-            conv_tabs.append(None)
-            pool_tabs.append(None)
-            up_tabs.append(None)
 
         host_stats = stats.cpu()
         if int(host_stats[:, 1].max()) != 0:

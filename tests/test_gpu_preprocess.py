@@ -209,3 +209,23 @@ def test_calibrate_neighbors_matches_reference_procedure(oracle):
     cumsum = np.cumsum(hists.T, axis=0)
     want = np.sum(cumsum < (0.8 * cumsum[hist_n - 1, :]), axis=0)
     assert np.array_equal(got, want)
+
+
+def test_pyramid_architecture_ending_on_a_strided_block(oracle):
+    """The schedule's corner case (reference finegrained_kpconv.py:340-409): the last block is strided, so its level
+    carries pool and upsample tables but the pooled points themselves are not appended."""
+    cfg = kpconv_config("modelnet", architecture=["simple", "resnetb", "resnetb_strided"], num_layers=1)
+    src, tgt, _ = synthetic.modelnet_pair(seed=8)
+    want = oracle.preprocess([src, tgt], cfg, impl=_impl(oracle))
+    meta = meta_to_numpy(Preprocessor(cfg)([cuda(src), cuda(tgt)]))
+    assert len(want["points"]) == len(meta["points"]) == 1
+    for key in ("points", "stack_lengths"):
+        assert np.array_equal(np.asarray(meta[key][0]), np.asarray(want[key][0]))
+    r = cfg.first_subsampling_dl * cfg.conv_radius
+    p, l = want["points"][0], want["stack_lengths"][0]
+    sub, sub_l = oracle.subsample_batch(p, l, 2 * r / cfg.conv_radius, impl=_impl(oracle))
+    from gpu_util import assert_rows_equal_up_to_ties
+    from test_oracle import tie_rows
+    assert_rows_equal_up_to_ties(meta["neighbors"][0], want["neighbors"][0], tie_rows(oracle, p, p, l, l, r))
+    assert_rows_equal_up_to_ties(meta["pools"][0], want["pools"][0], tie_rows(oracle, sub, p, sub_l, l, r))
+    assert_rows_equal_up_to_ties(meta["upsamples"][0], want["upsamples"][0], tie_rows(oracle, p, sub, l, sub_l, 2 * r))
