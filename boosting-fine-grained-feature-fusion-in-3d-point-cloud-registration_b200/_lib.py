@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkpreg_b200.so")
+LIB_PATH = os.environ.get("KPREG_B200_LIB") or os.path.join(_HERE, "libkpreg_b200.so")  # override: development A/B builds
 
 _c_i64 = ctypes.c_int64
 _c_int = ctypes.c_int
@@ -53,6 +53,11 @@ _SIGNATURES = {
     "kpreg_segment_norm_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_segment_norm_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
                                             _c_f32, _c_ptr, _c_int, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_chain_supported": (_c_int, [_c_int, _c_int]),
+    "kpreg_chain_pack_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_chain_pack": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_chain_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr, _c_int, _c_int,
+                                     _c_ptr]),
     "kpreg_kabsch": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f32, _c_int, _c_ptr, _c_ptr]),
 }
 

@@ -35,6 +35,8 @@ constexpr int KMAX = 16;             // kernel points handled per neighbour (ref
 constexpr int KSTRIDE = 20;          // floats per neighbour row of influences in shared memory: 16-byte aligned, conflict-free float4 stores
 constexpr int kGatherWarps = 4;      // warps (= queries in flight) per CTA
 bool g_gather_mma = true;            // aggregate on mma.sync (3xTF32); false = fp32 FFMA kernel (KPREG_GATHER_FFMA=1)
+bool g_no_c1 = false;                // KPREG_NO_C1=1: c_in == 1 goes through the generic gather + GEMM path (A/B measurements)
+bool g_gather_novec = false;         // KPREG_GATHER_NOVEC=1: scalar-load channel binding even for aligned rows (A/B measurements)
 
 __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ x, int64_t n_s, int c_in,
                                                       unsigned char* __restrict__ pos) {
@@ -161,10 +163,15 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather(
 // N = 8 channels per tile.  Every lane computes exactly the four influences of its A fragment
 // (kernel points g, g+8 x neighbours t, t+4 with g = lane/4, t = lane%4) — no influence is computed twice —
 // and loads its B fragment straight from the two neighbours' feature rows (8 lanes read 32 contiguous bytes).
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// 3xTF32 operand split x = hi + lo.  hi = x rounded to the nearest TF32 by integer arithmetic on the bit pattern (add half
+// an ulp of the 10-bit mantissa, clear the 13 low bits: two instructions; ptxas expands cvt.rna.tf32.f32 into an
+// add + Inf/NaN test + select, and the rounding of lo into four more).  lo = x - hi is exact in fp32 and is handed to the
+// tensor core as is: HMMA ignores the 13 low mantissa bits of a TF32 operand, i.e. truncates lo to 11 significant bits,
+// an error of at most 2^-21 |x|, below the lo*lo term 3xTF32 drops anyway.  (Inf stays Inf in hi and gives NaN in lo; finite
+// values within half a TF32 ulp of FLT_MAX round to Inf — neither occurs in feature data.)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -183,7 +190,13 @@ __device__ __forceinline__ float influence_one(float rx, float ry, float rz, flo
   return 1.0f;
 }
 
-template <typename IdxT, int NT>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
+// VEC (c_in a multiple of 4, 16-byte aligned rows): the MMA's N index is only a label, so column g of tile i is
+// bound to channel NT * g + i instead of 8 * i + g.  Lane g then needs NT CONTIGUOUS channels of each of its two
+// neighbour rows (float4 loads; the eight lanes sharing a neighbour read one contiguous 32 * NT-byte span), and
+// its D fragment covers the 2 * NT contiguous channels [2t * NT, 2t * NT + 2 NT) of rows g and g + 8 (float4 stores).
+// The index row of the next query is requested before the current query's work.  (Requesting the feature rows of k-step
+// s + 1 before the MMAs of k-step s was measured SLOWER on B200 — 5-9 % — through the registers it costs.)
+template <typename IdxT, int NT, bool VEC>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
 __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
@@ -198,45 +211,62 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
               k0z = k0_ok ? kernel_points[3 * g + 2] : 0.f;
   const float k1x = k1_ok ? kernel_points[3 * (g + 8)] : 0.f, k1y = k1_ok ? kernel_points[3 * (g + 8) + 1] : 0.f,
               k1z = k1_ok ? kernel_points[3 * (g + 8) + 2] : 0.f;
+  const int n_s32 = (int)n_s;  // the launcher routes n_s >= 2^31 to the FFMA kernel: support rows fit an int here
 
   // each CTA owns a CONTIGUOUS slice of the (spatially sorted) processing order, so the neighbourhoods its warps
   // gather overlap and stay in this SM's L1
   const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
   const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
-  for (int64_t it = (int64_t)blockIdx.x * per_cta + warp; it < it_end; it += kGatherWarps) {
-    const int64_t n = order ? (int64_t)order[it] : it;  // processing order only, never the result
+  int64_t it = (int64_t)blockIdx.x * per_cta + warp;
+  // index row (neighbours h = lane and h = lane + 32) of the query about to be processed, fetched one query ahead
+  int64_t n_nx = 0;
+  IdxT raw_nx[2] = {(IdxT)n_s32, (IdxT)n_s32};
+  if (it < it_end) {
+    n_nx = order ? (int64_t)order[it] : it;  // processing order only, never the result
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      if (lane + 32 * r < n_nbrs) raw_nx[r] = idx[n_nx * n_nbrs + lane + 32 * r];
+  }
+  for (; it < it_end; it += kGatherWarps) {
+    const int64_t n = n_nx;
+    const IdxT raw[2] = {raw_nx[0], raw_nx[1]};
+    if (it + kGatherWarps < it_end) {
+      n_nx = order ? (int64_t)order[it + kGatherWarps] : it + kGatherWarps;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) raw_nx[r] = lane + 32 * r < n_nbrs ? idx[n_nx * n_nbrs + lane + 32 * r] : (IdxT)n_s32;
+    }
     const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
-    // neighbours h = lane and h = lane + 32: index and relative position, fetched once, shuffled per k-step
-    int64_t jn[2];
+    // relative positions of this lane's two neighbours, fetched once and shuffled per k-step
+    int jn[2];
     float rx[2], ry[2], rz[2];
     int num = 0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const int h = lane + 32 * r;
-      int64_t j = n_s;
-      if (h < n_nbrs) j = (int64_t)idx[n * n_nbrs + h];
-      const bool valid = j >= 0 && j < n_s;
-      jn[r] = valid ? j : -1;
+      const bool valid = raw[r] >= 0 && raw[r] < (IdxT)n_s32;
+      const int j = valid ? (int)raw[r] : -1;
+      jn[r] = j;
       rx[r] = ry[r] = rz[r] = 0.f;
-      if (valid) { rx[r] = s_pts[3 * j] - qx; ry[r] = s_pts[3 * j + 1] - qy; rz[r] = s_pts[3 * j + 2] - qz; }
+      if (valid) { rx[r] = s_pts[3 * (int64_t)j] - qx; ry[r] = s_pts[3 * (int64_t)j + 1] - qy; rz[r] = s_pts[3 * (int64_t)j + 2] - qz; }
       num += __popc(__ballot_sync(0xffffffffu, valid && row_pos[j] != 0));
     }
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-    for (int h0 = 0; h0 < n_nbrs; h0 += 8) {
-      // neighbours of this lane's fragment columns: h0 + t and h0 + t + 4
+    // neighbour rows of this lane's fragment columns in k-step h0: h0 + t and h0 + t + 4 (-1 = shadow)
+    auto step_rows = [&](int h0, int& ja, int& jb) {
+      const int ha = h0 + t, hb = h0 + t + 4;  // (h >> 5) is warp-uniform per k-step: h0 is a multiple of 8
+      ja = __shfl_sync(0xffffffffu, (ha >> 5) ? jn[1] : jn[0], ha & 31);
+      jb = __shfl_sync(0xffffffffu, (hb >> 5) ? jn[1] : jn[0], hb & 31);
+    };
+    // A fragment of k-step h0: the four influences (k = g | g + 8) x (h = h0 + t | h0 + t + 4), split hi / lo
+    auto step_influences = [&](int h0, bool va, bool vb, float (&a_hi)[4], float (&a_lo)[4]) {
       const int ha = h0 + t, hb = h0 + t + 4;
-      const int ra = ha >> 5, rb = hb >> 5;  // warp-uniform per k-step (h0 is a multiple of 8)
-      const int64_t ja = __shfl_sync(0xffffffffu, ra ? jn[1] : jn[0], ha & 31);
-      const int64_t jb = __shfl_sync(0xffffffffu, rb ? jn[1] : jn[0], hb & 31);
+      const int ra = ha >> 5, rb = hb >> 5;
       const float ax = __shfl_sync(0xffffffffu, ra ? rx[1] : rx[0], ha & 31), ay = __shfl_sync(0xffffffffu, ra ? ry[1] : ry[0], ha & 31),
                   az = __shfl_sync(0xffffffffu, ra ? rz[1] : rz[0], ha & 31);
       const float bx = __shfl_sync(0xffffffffu, rb ? rx[1] : rx[0], hb & 31), by = __shfl_sync(0xffffffffu, rb ? ry[1] : ry[0], hb & 31),
                   bz = __shfl_sync(0xffffffffu, rb ? rz[1] : rz[0], hb & 31);
-      const bool va = ja >= 0, vb = jb >= 0;
-      if (!__any_sync(0xffffffffu, va || vb)) continue;  // eight shadow neighbours: nothing to add
       float w[4], d2[4];
       w[0] = influence_one(ax, ay, az, k0x, k0y, k0z, inv_extent, extent, influence, d2[0]);  // (k = g,     h = t)
       w[1] = influence_one(ax, ay, az, k1x, k1y, k1z, inv_extent, extent, influence, d2[1]);  // (k = g + 8, h = t)
@@ -263,25 +293,67 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
           if (best_k != g + 8) w[2 * hh + 1] = 0.f;
         }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tf32_split(w[i], a_hi[i], a_lo[i]);
+    };
+    auto mma3 = [&](float (&d)[4], const float (&a_hi)[4], const float (&a_lo)[4], float b0, float b1) {
+      float b0h, b0l, b1h, b1l;
+      tf32_split(b0, b0h, b0l);
+      tf32_split(b1, b1h, b1l);
+      mma_tf32(d, a_lo, b0h, b1h);
+      mma_tf32(d, a_hi, b0l, b1l);
+      mma_tf32(d, a_hi, b0h, b1h);
+    };
+    auto comp4 = [](const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); };
+
+    for (int h0 = 0; h0 < n_nbrs; h0 += 8) {
+      int ja, jb;
+      step_rows(h0, ja, jb);
+      const bool va = ja >= 0, vb = jb >= 0;
+      if (!__any_sync(0xffffffffu, va || vb)) continue;  // eight shadow neighbours: nothing to add
       float a_hi[4], a_lo[4];
+      step_influences(h0, va, vb, a_hi, a_lo);
+      const float* __restrict__ xa = x + (int64_t)(va ? ja : 0) * c_in;
+      const float* __restrict__ xb = x + (int64_t)(vb ? jb : 0) * c_in;
+      if constexpr (VEC) {
+        float4 fa[NT / 4], fb[NT / 4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a_hi[i] = tf32_rn(w[i]); a_lo[i] = tf32_rn(w[i] - a_hi[i]); }
-      const float* __restrict__ xa = x + (va ? ja : 0) * c_in;
-      const float* __restrict__ xb = x + (vb ? jb : 0) * c_in;
+        for (int m = 0; m < NT / 4; ++m) {
+          const int c = NT * g + 4 * m;
+          fa[m] = (va && c < c_in) ? __ldg(reinterpret_cast<const float4*>(xa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          fb[m] = (vb && c < c_in) ? __ldg(reinterpret_cast<const float4*>(xb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        const int c = 8 * i + g;
-        const float b0 = (va && c < c_in) ? xa[c] : 0.f;
-        const float b1 = (vb && c < c_in) ? xb[c] : 0.f;
-        const float b0h = tf32_rn(b0), b1h = tf32_rn(b1);
-        const float b0l = tf32_rn(b0 - b0h), b1l = tf32_rn(b1 - b1h);
-        mma_tf32(acc[i], a_lo, b0h, b1h);
-        mma_tf32(acc[i], a_hi, b0l, b1l);
-        mma_tf32(acc[i], a_hi, b0h, b1h);
+        for (int m = 0; m < NT / 4; ++m)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mma3(acc[4 * m + e], a_hi, a_lo, comp4(fa[m], e), comp4(fb[m], e));
+      } else {
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          const int c = 8 * i + g;
+          mma3(acc[i], a_hi, a_lo, (va && c < c_in) ? xa[c] : 0.f, (vb && c < c_in) ? xb[c] : 0.f);
+        }
       }
     }
     // D fragment: rows (kernel points) g and g + 8, columns (channels) 8 i + 2 t, + 1
     float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in;
+    if constexpr (VEC) {
+      // D fragment under the VEC binding: acc[i][0|2] <-> channel 2t * NT + i, acc[i][1|3] <-> channel (2t + 1) * NT + i
+#pragma unroll
+      for (int m = 0; m < NT / 4; ++m) {
+        const int ce = 2 * t * NT + 4 * m, co = (2 * t + 1) * NT + 4 * m;
+        if (ce < c_in) {
+          if (k0_ok) *reinterpret_cast<float4*>(arow + g * c_in + ce) = make_float4(acc[4 * m][0], acc[4 * m + 1][0], acc[4 * m + 2][0], acc[4 * m + 3][0]);
+          if (k1_ok) *reinterpret_cast<float4*>(arow + (g + 8) * c_in + ce) = make_float4(acc[4 * m][2], acc[4 * m + 1][2], acc[4 * m + 2][2], acc[4 * m + 3][2]);
+        }
+        if (co < c_in) {
+          if (k0_ok) *reinterpret_cast<float4*>(arow + g * c_in + co) = make_float4(acc[4 * m][1], acc[4 * m + 1][1], acc[4 * m + 2][1], acc[4 * m + 3][1]);
+          if (k1_ok) *reinterpret_cast<float4*>(arow + (g + 8) * c_in + co) = make_float4(acc[4 * m][3], acc[4 * m + 1][3], acc[4 * m + 2][3], acc[4 * m + 3][3]);
+        }
+      }
+      if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+      continue;
+    }
     const bool pair_ok = (c_in & 1) == 0;  // (row * c_in + even column) is then 8-byte aligned: one float2 store
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
@@ -301,6 +373,123 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
       }
     }
     if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+  }
+}
+
+// ---- c_in == 1 (the encoder's first block: a single input feature per point) ----------------------------
+// With one channel the aggregate is 15 numbers per query and the contraction a [15] x [15, c_out] product, so the whole
+// operator is one kernel: a lane per neighbour evaluates the K influences (fp32 FFMA), a transposing butterfly leaves
+// the total of kernel point k in lanes 2k / 2k+1 (16 shuffles), and every lane finishes c_out / 32 output channels
+// from register-resident weights.  No aggregate, no row predicate pass (sum_c x > 0 is x > 0) and no GEMM launch.
+template <typename IdxT, int CPL>  // CPL = output channels per lane (c_out <= 32 * CPL)
+__global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1(
+    const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
+    const float* __restrict__ kernel_points, const float* __restrict__ weights, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
+    int c_out, float extent, int influence, int aggregation, float* __restrict__ out, const int32_t* __restrict__ order) {
+  __shared__ float s_kp[KMAX * 3];
+  __shared__ float s_wt[KMAX][32 * CPL];  // weights, zero-padded: lane reads column lane + 32 cc (conflict-free)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < KMAX * 3) s_kp[threadIdx.x] = threadIdx.x < n_kpts * 3 ? kernel_points[threadIdx.x] : 0.f;
+  for (int i = threadIdx.x; i < KMAX * 32 * CPL; i += blockDim.x) {
+    const int k = i / (32 * CPL), c = i % (32 * CPL);
+    s_wt[k][c] = (k < n_kpts && c < c_out) ? weights[k * c_out + c] : 0.f;
+  }
+  __syncthreads();
+  const float inv_extent = 1.0f / extent;
+  // neighbours 0..31: a lane each.  Neighbours 32..: a lane each, or — for a short tail (H = 40: eight neighbours) in
+  // 'sum' mode — eight lanes per quarter of the kernel points instead of 24 idle lanes.
+  const int rem = n_nbrs - 32;
+  const bool quarter = rem > 0 && rem <= 8 && aggregation == 0;
+  const int h_a = lane, h_b = 32 + (quarter ? (lane & 7) : lane), q4 = (lane >> 3) * 4;
+  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  int64_t it = (int64_t)blockIdx.x * per_cta + warp;
+  // the index row of the NEXT query is fetched while the current one is processed
+  int64_t n_nx = 0, ja_nx = n_s, jb_nx = n_s;
+  if (it < it_end) {
+    n_nx = order ? (int64_t)order[it] : it;
+    if (h_a < n_nbrs) ja_nx = (int64_t)idx[n_nx * n_nbrs + h_a];
+    if (h_b < n_nbrs) jb_nx = (int64_t)idx[n_nx * n_nbrs + h_b];
+  }
+  for (; it < it_end; it += kGatherWarps) {
+    const int64_t n = n_nx, ja = ja_nx, jb = jb_nx;  // processing order only, never the result
+    if (it + kGatherWarps < it_end) {
+      n_nx = order ? (int64_t)order[it + kGatherWarps] : it + kGatherWarps;
+      ja_nx = h_a < n_nbrs ? (int64_t)idx[n_nx * n_nbrs + h_a] : n_s;
+      jb_nx = h_b < n_nbrs ? (int64_t)idx[n_nx * n_nbrs + h_b] : n_s;
+    }
+    const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
+    const bool va = ja >= 0 && ja < n_s, vb = jb >= 0 && jb < n_s;
+    float xa = 0.f, ax = 0.f, ay = 0.f, az = 0.f, xb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    if (va) { xa = x[ja]; ax = s_pts[3 * ja] - qx; ay = s_pts[3 * ja + 1] - qy; az = s_pts[3 * ja + 2] - qz; }
+    if (vb) { xb = x[jb]; bx = s_pts[3 * jb] - qx; by = s_pts[3 * jb + 1] - qy; bz = s_pts[3 * jb + 2] - qz; }
+    int num = __popc(__ballot_sync(0xffffffffu, va && xa > 0.f));
+    if (rem > 0) num += __popc(__ballot_sync(0xffffffffu, vb && xb > 0.f && (!quarter || lane < 8)));
+    float v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) v[k] = 0.f;
+    if (va) {
+      float w[KMAX];
+      influences(ax, ay, az, s_kp, n_kpts, extent, influence, aggregation, w);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) v[k] = w[k] * xa;
+    }
+    if (quarter) {
+      float u[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = q4 + kk;
+        float d2;
+        const float w = influence_one(bx, by, bz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_extent, extent, influence, d2);
+        u[kk] = (vb && k < n_kpts) ? w * xb : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) v[k] += ((k & ~3) == q4) ? u[k & 3] : 0.f;
+    } else if (vb) {
+      float w[KMAX];
+      influences(bx, by, bz, s_kp, n_kpts, extent, influence, aggregation, w);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) v[k] = fmaf(w[k], xb, v[k]);
+    }
+    // transposing butterfly: after offsets 16, 8, 4, 2 a lane holds one kernel point's partial, k = lane >> 1
+    float v8[8], v4[4], v2[2];
+    {
+      const bool up = (lane & 16) != 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = (up ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 8], 16);
+    }
+    {
+      const bool up = (lane & 8) != 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v4[i] = (up ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, up ? v8[i] : v8[i + 4], 8);
+    }
+    {
+      const bool up = (lane & 4) != 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) v2[i] = (up ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 4);
+    }
+    float tot;
+    {
+      const bool up = (lane & 2) != 0;
+      tot = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up ? v2[0] : v2[1], 2);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    }
+    float o[CPL];
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) o[cc] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const float ak = __shfl_sync(0xffffffffu, tot, 2 * k);
+#pragma unroll
+      for (int cc = 0; cc < CPL; ++cc) o[cc] = fmaf(ak, s_wt[k][lane + 32 * cc], o[cc]);
+    }
+    const float inv = 1.0f / (float)max(num, 1);
+    float* __restrict__ orow = out + n * (int64_t)c_out;
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) {
+      const int c = lane + 32 * cc;
+      if (c < c_out) orow[c] = o[cc] * inv;
+    }
   }
 }
 
@@ -499,17 +688,19 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   if (blocks > cap) blocks = cap;
   const IdxT* ip = static_cast<const IdxT*>(idx);
   ProfScope prof(KPREG_FAM_GATHER, stream);
-  if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && g_gather_mma) {
-#define KP_GATHER_MMA(NT)                                                                                                       \
-  k_kpconv_gather_mma<IdxT, NT><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs,   \
-                                                                          n_kpts, c_in, extent, influence, aggregation, agg,    \
-                                                                          inv_num, order)
-    if (c_in <= 8) KP_GATHER_MMA(1);
-    else if (c_in <= 16) KP_GATHER_MMA(2);
-    else if (c_in <= 32) KP_GATHER_MMA(4);
-    else if (c_in <= 64) KP_GATHER_MMA(8);
-    else if (c_in <= 128) KP_GATHER_MMA(16);
-    else KP_GATHER_MMA(32);
+  if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && n_s < ((int64_t)1 << 31) && g_gather_mma) {
+#define KP_GATHER_MMA(NT, VEC)                                                                                                 \
+  k_kpconv_gather_mma<IdxT, NT, VEC><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s,     \
+                                                                               n_nbrs, n_kpts, c_in, extent, influence,        \
+                                                                               aggregation, agg, inv_num, order)
+    // float4 path: whole rows of x and of the aggregate are 16-byte aligned
+    const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
+    if (c_in <= 8) KP_GATHER_MMA(1, false);
+    else if (c_in <= 16) KP_GATHER_MMA(2, false);
+    else if (c_in <= 32) { if (vec) KP_GATHER_MMA(4, true); else KP_GATHER_MMA(4, false); }
+    else if (c_in <= 64) { if (vec) KP_GATHER_MMA(8, true); else KP_GATHER_MMA(8, false); }
+    else if (c_in <= 128) { if (vec) KP_GATHER_MMA(16, true); else KP_GATHER_MMA(16, false); }
+    else { if (vec) KP_GATHER_MMA(32, true); else KP_GATHER_MMA(32, false); }
 #undef KP_GATHER_MMA
     KP_LAUNCH_CHECK();
     return KPREG_OK;
@@ -566,6 +757,10 @@ struct GatherModeInit {
   GatherModeInit() {
     const char* e = getenv("KPREG_GATHER_FFMA");
     if (e && e[0] == '1') kpreg::g_gather_mma = false;
+    e = getenv("KPREG_GATHER_NOVEC");
+    if (e && e[0] == '1') kpreg::g_gather_novec = true;
+    e = getenv("KPREG_NO_C1");
+    if (e && e[0] == '1') kpreg::g_no_c1 = true;
   }
 } g_gather_mode_init;
 }  // namespace
@@ -588,6 +783,21 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   if (n_s > 0 && (!s_pts || !x)) return KPREG_E_INVALID;
   if (n_nbrs > 0 && !idx) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (c_in == 1 && c_out <= 128 && n_nbrs <= 64 && gemm != 2 && n_s > 0 && !g_no_c1) {
+    // single input channel: gather, contraction and normalisation in one kernel (raw [K, 1, c_out] weights)
+    int blocks = ceil_div(n_q, kGatherWarps);
+    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+    ProfScope prof(KPREG_FAM_GATHER, stream);
+#define KP_C1(IdxT, CPL)                                                                                                        \
+  k_kpconv_c1<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x, kernel_points, \
+                                                                   weights, n_q, n_s, n_nbrs, n_kpts, c_out, kp_extent, influence, \
+                                                                   aggregation, out, order)
+    if (idx64) { if (c_out <= 32) KP_C1(int64_t, 1); else if (c_out <= 64) KP_C1(int64_t, 2); else KP_C1(int64_t, 4); }
+    else { if (c_out <= 32) KP_C1(int32_t, 1); else if (c_out <= 64) KP_C1(int32_t, 2); else KP_C1(int32_t, 4); }
+#undef KP_C1
+    KP_LAUNCH_CHECK();
+    return KPREG_OK;
+  }
   KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 0);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
   if (n_s > 0) {

@@ -33,6 +33,8 @@ DEFAULT_GEMM = 1
 # inference (no autograd) on CUDA: run the blocks' Linear / InstanceNorm / eval-BatchNorm / activation glue on
 # the fused CUDA kernels (kpreg_linear_forward, kpreg_segment_norm_forward); otherwise stock PyTorch ops
 FUSED_GLUE = True
+# res2net's chained layers in one register-resident kernel (kpreg_chain_forward) where the width allows it
+CHAIN_KERNEL = True
 
 
 def _fused(x: torch.Tensor) -> bool:

@@ -356,3 +356,41 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
                                         ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_segment_norm_forward")
     return out
+
+
+class ChainPack:
+    """The folded weights / shifts of a res2net chain arranged once in the fragment order kpreg_chain_forward reads."""
+
+    def __init__(self, weights: torch.Tensor, shifts: torch.Tensor):
+        lib = _lib.load()
+        weights, shifts = _f32c(weights, "weights"), _f32c(shifts, "shifts")
+        self.n_layers, self.width = int(weights.shape[0]), int(weights.shape[1])
+        if weights.shape[2] != self.width or tuple(shifts.shape) != (self.n_layers, self.width):
+            raise RuntimeError("chain: weights [L, w, w] and shifts [L, w] expected")
+        nbytes = _lib.size_query("kpreg_chain_pack_bytes", self.width, self.n_layers)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=weights.device)
+        rc = lib.kpreg_chain_pack(weights.data_ptr(), shifts.data_ptr(), self.width, self.n_layers, self.buf.data_ptr(), nbytes,
+                                  _lib.stream_ptr(weights.device))
+        _lib.check(rc, "kpreg_chain_pack")
+
+
+def chain_supported(width: int, n_layers: int) -> bool:
+    return bool(_lib.load().kpreg_chain_supported(int(width), int(n_layers)))
+
+
+def chain_forward(t: torch.Tensor, pack: ChainPack, z: torch.Tensor, x_copy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """res2net's chained layers over conv1's output t [M, (L+1) w] into z [M, >= (L+1) w (+ c_x)] (kpreg_chain_forward)."""
+    lib = _lib.load()
+    t, ld_t = _rows(t, "t")
+    _lib.require_cuda(z, "z")
+    if z.dtype != torch.float32 or z.dim() != 2 or z.stride(1) != 1:
+        raise RuntimeError("chain: z must be a float32 matrix with contiguous rows")
+    m = t.shape[0]
+    x_ptr, ld_x, c_x = None, 0, 0
+    if x_copy is not None:
+        x_copy, ld_x = _rows(x_copy, "x_copy")
+        x_ptr, c_x = x_copy.data_ptr(), int(x_copy.shape[1])
+    rc = lib.kpreg_chain_forward(t.data_ptr(), ld_t, pack.buf.data_ptr(), pack.width, pack.n_layers, m, z.data_ptr(),
+                                 int(z.stride(0)) if m > 1 else int(z.shape[1]), x_ptr, ld_x, c_x, _lib.stream_ptr(t.device))
+    _lib.check(rc, "kpreg_chain_forward")
+    return z

@@ -52,6 +52,18 @@ class my_Bottle2neck(nn.Module):
         self.scale = scale
         self.width = width
 
+    def _chain_pack(self):
+        """Folded weights / shifts of convs[i] / bns[i], packed once for kpreg_chain_forward (cached until a
+        parameter or running statistic changes)."""
+        from . import ops
+        folded = [_folded(self.convs[i], self.bns[i]) for i in range(self.nums)]
+        key = tuple(self.bns[i]._kpreg_folded[0] for i in range(self.nums))
+        cache = getattr(self, "_kpreg_chain", None)
+        if cache is None or cache[0] != key:
+            cache = (key, ops.ChainPack(torch.stack([f[0] for f in folded]), torch.stack([f[1] for f in folded])))
+            self._kpreg_chain = cache
+        return cache[1]
+
     def _fused_forward(self, x):
         """Inference on CUDA: every Linear + eval-BatchNorm (+ ReLU) is one tensor-core GEMM with a fused
         epilogue; each chained layer also emits `its output + the next group` (the next layer's input); the
@@ -65,20 +77,27 @@ class my_Bottle2neck(nn.Module):
         fuse_res = self.downsample is not None and x.shape[1] % 4 == 0
         k_cat = w * n_groups
         z = torch.empty((t.shape[0], k_cat + (x.shape[1] if fuse_res else 0)), dtype=t.dtype, device=t.device)
-        scratch = [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
-        inp = t[:, :w]
-        for i in range(self.nums):
-            wt, sh = _folded(self.convs[i], self.bns[i])
-            nxt = i + 1 < self.nums
-            ops.linear_forward(inp, wt, None, sh, act="relu", out=z[:, i * w:(i + 1) * w],
-                               out2=scratch[i & 1] if nxt else None, addend=t[:, (i + 1) * w:(i + 2) * w] if nxt else None,
-                               gemm=gemm)
-            inp = scratch[i & 1]
-        z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
+        chain = kb.CHAIN_KERNEL and self.nums == n_groups - 1 and ops.chain_supported(w, self.nums)
+        if chain:
+            # all chained layers in one kernel: a warp keeps its rows of the running activation in registers,
+            # t is read once, z written once (the pass-through group and the copy of x included)
+            ops.chain_forward(t, self._chain_pack(), z, x if fuse_res else None)
+        else:
+            scratch = [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
+            inp = t[:, :w]
+            for i in range(self.nums):
+                wt, sh = _folded(self.convs[i], self.bns[i])
+                nxt = i + 1 < self.nums
+                ops.linear_forward(inp, wt, None, sh, act="relu", out=z[:, i * w:(i + 1) * w],
+                                   out2=scratch[i & 1] if nxt else None, addend=t[:, (i + 1) * w:(i + 2) * w] if nxt else None,
+                                   gemm=gemm)
+                inp = scratch[i & 1]
+            z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
         w3, b3 = _folded(self.conv3, self.bn3)
         if fuse_res:
             # relu(bn3(cat W3^T) + bn_d(x Wd^T)) = relu([cat | x] [W3' | Wd']^T + b3' + bd')
-            z[:, k_cat:] = x
+            if not chain:
+                z[:, k_cat:] = x
             wd, bd = _folded(self.downsample[0], self.downsample[1])
             key = (self.bn3._kpreg_folded[0], self.downsample[1]._kpreg_folded[0])
             cache = getattr(self, "_kpreg_joint", None)

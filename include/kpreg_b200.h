@@ -199,6 +199,29 @@ KPREG_API int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t*
                                          int channels, float eps, const float* residual, int ld_res, int act, float slope,
                                          float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The hierarchical chain of my_Bottle2neck in one kernel (models/backbone_kpconv/res2net.py:137-150):
+ *     sp = t_0;  for i in 0 .. n_layers-1:  sp = relu(sp W_i^T + shift_i);  z_i = sp;  sp = sp + t_{i+1}
+ * with t_g = t[:, g*width : (g+1)*width] (conv1's output, n_layers + 1 groups), W_i / shift_i the i-th
+ * convs[i] / bns[i] pair with the eval-mode BatchNorm1d folded in.  z[:, i*width : (i+1)*width] = z_i for
+ * i < n_layers, z[:, n_layers*width : (n_layers+1)*width] = t_{n_layers} (the group the reference passes through
+ * unchanged, :151-152), and — when x_copy is given — z[:, (n_layers+1)*width : +c_x] = x_copy (the block input,
+ * so that conv3 and the residual projection run as one GEMM over the concatenation).
+ * A warp keeps 32 rows of sp in registers across all layers (mma.sync 3xTF32, weights resident in shared memory):
+ * t is read once and z written once.
+ *   kpreg_chain_supported: 1 if (width, n_layers) is served by this kernel (even width, ceil(width/8) in
+ *       {2,4,7,8}, packed weights <= 200 KiB), else 0 — the caller then runs the layers through kpreg_linear_forward.
+ *   kpreg_chain_pack: arrange weights [n_layers, width, width] (nn.Linear layout [out, in], BN scale folded in)
+ *       and shifts [n_layers, width] once into the fragment order the kernel reads (kpreg_chain_pack_bytes bytes).
+ *   kpreg_chain_forward: t [M, ld_t], z [M, ld_z] (ld_t, ld_z even, 8-byte aligned bases), x_copy [M, ld_x] or NULL.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_chain_supported(int width, int n_layers);
+KPREG_API int kpreg_chain_pack_bytes(int width, int n_layers, size_t* bytes);
+KPREG_API int kpreg_chain_pack(const float* weights, const float* shifts, int width, int n_layers, void* pack,
+                               size_t pack_bytes, void* stream);
+KPREG_API int kpreg_chain_forward(const float* t, int ld_t, const void* pack, int width, int n_layers, int64_t m_rows,
+                                  float* z, int ld_z, const float* x_copy, int ld_x, int c_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,3 +88,69 @@ def test_segment_norm_matches_instance_norm(lens, c):
     got2 = ops.segment_norm(x, lens_t, residual=res, act="leaky_relu", slope=0.1)
     want2 = torch.nn.functional.leaky_relu(want + res.double(), 0.1)
     assert rel_err(got2.cpu().numpy(), want2.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("w,n_layers,m,c_x", [(28, 7, 5000, 32), (56, 7, 3001, 64), (14, 7, 257, 16), (16, 3, 31, 0), (64, 5, 700, 30),
+                                              (56, 7, 256, 0)])
+def test_chain_kernel_matches_layerwise_reference(w, n_layers, m, c_x):
+    """res2net's chained layers in one kernel (kpreg_chain_forward) vs the layer-by-layer definition in fp64
+    (reference res2net.py:137-152): every out_i, the pass-through group and the copy of the block input."""
+    torch.manual_seed(w * 100 + m)
+    groups = n_layers + 1
+    assert ops.chain_supported(w, n_layers)
+    wide = torch.randn(m, groups * w + 6, device="cuda")
+    t = wide[:, 2:2 + groups * w]                                  # a column slice: row pitch != groups * w
+    weights = torch.randn(n_layers, w, w, device="cuda") / w ** 0.5
+    shifts = torch.randn(n_layers, w, device="cuda") * 0.3
+    x = torch.randn(m, c_x, device="cuda") if c_x else None
+    z = torch.full((m, groups * w + c_x + 4), 7.0, device="cuda")  # trailing guard columns must stay untouched
+    ops.chain_forward(t, ops.ChainPack(weights, shifts), z, x)
+    td, want = t.double(), []
+    sp = td[:, :w]
+    for i in range(n_layers):
+        sp = torch.relu(sp @ weights[i].double().t() + shifts[i].double())
+        want.append(sp)
+        sp = sp + td[:, (i + 1) * w:(i + 2) * w]
+    want.append(td[:, n_layers * w:])
+    if c_x:
+        want.append(x.double())
+    want = torch.cat(want, 1)
+    got = z[:, :want.shape[1]]
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+    assert torch.equal(got[:, n_layers * w:], want[:, n_layers * w:].float())   # copies are exact
+    assert float((z[:, want.shape[1]:] - 7.0).abs().max()) == 0.0
+
+
+def test_chain_kernel_unsupported_widths_are_reported():
+    assert not ops.chain_supported(27, 7)      # odd width
+    assert not ops.chain_supported(112, 7)     # wider than the register-resident kernel serves
+    assert not ops.chain_supported(64, 7)      # packed weights exceed shared memory
+
+
+def test_bottleneck_fused_chain_matches_stock_layers():
+    """my_Bottle2neck inference: chain kernel on / off / stock PyTorch layers give the same features."""
+    from kpreg_b200 import kpconv_blocks
+    from kpreg_b200.res2net import my_Bottle2neck, my_res2Net
+    torch.manual_seed(3)
+    net = my_res2Net(my_Bottle2neck, 32, 128, baseWidth=14, scale=8).cuda().eval()
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.2)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    x = torch.randn(3333, 32, device="cuda")
+    with torch.no_grad():
+        kpconv_blocks.FUSED_GLUE = False
+        try:
+            stock = net(x)
+        finally:
+            kpconv_blocks.FUSED_GLUE = True
+        chain = net(x)
+        kpconv_blocks.CHAIN_KERNEL = False
+        try:
+            layers = net(x)
+        finally:
+            kpconv_blocks.CHAIN_KERNEL = True
+    assert rel_err(chain.cpu().numpy(), stock.cpu().numpy()) < 1e-5
+    assert rel_err(layers.cpu().numpy(), stock.cpu().numpy()) < 1e-5

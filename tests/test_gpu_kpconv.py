@@ -49,7 +49,7 @@ def test_max_pool_forward_backward(golden_modelnet):
     assert rel_err(x.grad.cpu().numpy(), g["bw_maxpool_dx"]) < 1e-6
 
 
-@pytest.mark.parametrize("c_in,c_out", [(1, 64), (32, 32), (64, 64), (128, 128), (256, 256), (40, 24)])
+@pytest.mark.parametrize("c_in,c_out", [(1, 64), (32, 32), (64, 64), (128, 128), (256, 256), (40, 24), (30, 16), (100, 8)])
 def test_kpconv_forward_matches_oracle_channel_sweep(oracle, golden_modelnet, c_in, c_out):
     """Every channel width the 3DMatch encoder uses (SURVEY.md §8a call table), + an odd one."""
     g = golden_modelnet
@@ -61,6 +61,30 @@ def test_kpconv_forward_matches_oracle_channel_sweep(oracle, golden_modelnet, c_
     want = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.06)
     got = ops.kpconv_forward(cuda(q), cuda(s), cuda(idx), cuda(x), cuda(w), cuda(kp), 0.06, gemm=0)
     assert rel_err(got.cpu().numpy(), want.numpy()) < TOL
+
+
+@pytest.mark.parametrize("n_nbrs", [5, 32, 40, 64])
+@pytest.mark.parametrize("agg,c_out", [("sum", 64), ("sum", 24), ("closest", 128)])
+def test_kpconv_single_input_channel_fused_kernel(oracle, golden_modelnet, n_nbrs, agg, c_out):
+    """c_in == 1 (the encoder's first block) runs gather + contraction + normalisation in one kernel: arbitrary
+    feature values (negative and zero rows do not count in the normaliser), shadow indices anywhere in the row,
+    widths that exercise the full-round, masked-round and short-tail (H = 40) paths."""
+    g = golden_modelnet
+    rng = np.random.default_rng(n_nbrs + c_out)
+    q = s = g["mn_points_0"]
+    n = s.shape[0]
+    near = g["mn_neighbors_0"]
+    idx = rng.integers(0, n + 1, size=(n, n_nbrs))                      # n == shadow
+    w0 = min(near.shape[1], n_nbrs)
+    idx[:, :w0] = near[:, :w0]                                          # real neighbours first: non-zero influences
+    x = rng.normal(size=(n, 1)).astype(np.float32)
+    x[::5] = 0.0
+    w = (rng.normal(size=(15, 1, c_out)) / 4).astype(np.float32)
+    kp = g["op_linear_sum_kp"] * 0.5
+    want = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.06, aggregation_mode=agg)
+    for dt in (torch.int64, torch.int32):
+        got = ops.kpconv_forward(cuda(q), cuda(s), cuda(idx, dt), cuda(x), cuda(w), cuda(kp), 0.06, aggregation=agg, gemm=1)
+        assert rel_err(got.cpu().numpy(), want.numpy()) < TOL
 
 
 def test_normalisation_counts_positive_feature_sums(oracle, golden_modelnet):
