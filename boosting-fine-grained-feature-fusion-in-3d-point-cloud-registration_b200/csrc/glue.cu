@@ -16,7 +16,8 @@ namespace kpreg {
 
 int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
                    const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
-                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, cudaStream_t stream);
+                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
+                   int post_act, cudaStream_t stream);
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) k_linear_simple(const float* __restrict__
                                                        const float* __restrict__ col_shift, const float* __restrict__ residual,
                                                        int ld_res, int act, float slope, float* __restrict__ out, int ldc,
                                                        float* __restrict__ out2, int ld2, const float* __restrict__ addend,
-                                                       int ld_add) {
+                                                       int ld_add, const float* __restrict__ post_res, int ld_post, int post_act) {
   const int64_t total = m_rows * (int64_t)n_dim;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / n_dim;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_linear_simple(const float* __restrict__
     if (col_shift) acc += col_shift[n];
     if (residual) acc += residual[m * ld_res + n];
     acc = activate(acc, act, slope);
+    if (post_res) acc = activate(acc + post_res[m * ld_post + n], post_act, slope);
     out[m * ldc + n] = acc;
     if (out2) out2[m * ld2 + n] = acc + addend[m * ld_add + n];
   }
@@ -199,8 +201,10 @@ extern "C" int kpreg_split_weights(const float* weight, int k_dim, int n_dim, in
 extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
                                     const float* col_scale, const float* col_shift, const float* residual, int ld_res, int act,
                                     float slope, float* out, int ldc, float* out2, int ld2, const float* addend, int ld_add,
-                                    int gemm, void* workspace, size_t workspace_bytes, void* stream_) {
+                                    const float* post_residual, int ld_post, int post_act, int gemm, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
   if (m_rows < 0 || k_dim < 1 || n_dim < 1 || ldx < k_dim || ldc < n_dim || act < 0 || act > 2) return KPREG_E_INVALID;
+  if (post_act < 0 || post_act > 2 || (post_residual && ld_post < n_dim)) return KPREG_E_INVALID;
   if (m_rows == 0) return KPREG_OK;
   if (!x || !weight || !out || (out2 && !addend)) return KPREG_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -209,7 +213,7 @@ extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight
     // `weight` already is the split operand pair produced by kpreg_split_weights
     if (!gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x)) return KPREG_E_INVALID;
     return launch_gemm_tc(x, ldx, weight, out, ldc, m_rows, k_dim, n_dim, nullptr, col_scale, col_shift, residual, ld_res, act,
-                          slope, out2, ld2, addend, ld_add, stream);
+                          slope, out2, ld2, addend, ld_add, post_residual, ld_post, post_act, stream);
   }
   if (gemm == 1 && gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x)) {
     if (!workspace || workspace_bytes < kpconv_gemm_tc_weight_bytes(k_dim, n_dim)) return KPREG_E_WORKSPACE;
@@ -217,12 +221,12 @@ extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight
     int rc = kpconv_gemm_tc_prepare_weights(weight, k_dim, n_dim, 0, w_split, stream);
     if (rc) return rc;
     return launch_gemm_tc(x, ldx, w_split, out, ldc, m_rows, k_dim, n_dim, nullptr, col_scale, col_shift, residual, ld_res, act,
-                          slope, out2, ld2, addend, ld_add, stream);
+                          slope, out2, ld2, addend, ld_add, post_residual, ld_post, post_act, stream);
   }
   int blocks = ceil_div(m_rows * (int64_t)n_dim, 256);
   if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
   k_linear_simple<<<blocks, 256, 0, stream>>>(x, ldx, weight, m_rows, k_dim, n_dim, col_scale, col_shift, residual, ld_res, act,
-                                              slope, out, ldc, out2, ld2, addend, ld_add);
+                                              slope, out, ldc, out2, ld2, addend, ld_add, post_residual, ld_post, post_act);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }

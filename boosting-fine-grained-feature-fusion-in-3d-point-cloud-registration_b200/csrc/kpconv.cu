@@ -24,7 +24,8 @@ namespace kpreg {
 // kpconv_gemm.cu: tcgen05 3xTF32 GEMM
 int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
                    const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
-                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, cudaStream_t stream);
+                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
+                   int post_act, cudaStream_t stream);
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
@@ -815,13 +816,13 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
     // `weights` already is the split operand pair produced by kpreg_split_weights(transpose = 1)
     if (!gemm_tc_supported(n_q, kd, c_out, kd, w.agg)) return KPREG_E_INVALID;
     return launch_gemm_tc(w.agg, kd, weights, out, c_out, n_q, kd, c_out, w.inv_num, nullptr, nullptr, nullptr, 0, 0, 0.f,
-                          nullptr, 0, nullptr, 0, stream);
+                          nullptr, 0, nullptr, 0, nullptr, 0, 0, stream);
   }
   if (gemm == 1 && gemm_tc_supported(n_q, kd, c_out, kd, w.agg)) {
     rc = kpconv_gemm_tc_prepare_weights(weights, kd, c_out, 1, w.w_split, stream);
     if (rc) return rc;
     return launch_gemm_tc(w.agg, kd, w.w_split, out, c_out, n_q, kd, c_out, w.inv_num, nullptr, nullptr, nullptr, 0, 0, 0.f,
-                          nullptr, 0, nullptr, 0, stream);
+                          nullptr, 0, nullptr, 0, nullptr, 0, 0, stream);
   }
   return launch_gemm<false, false>(w.agg, weights, out, w.inv_num, n_q, c_out, kd, 1, stream);
 }

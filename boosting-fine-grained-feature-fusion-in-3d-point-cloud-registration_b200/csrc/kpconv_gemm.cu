@@ -25,6 +25,7 @@
 //             residual / activation with coalesced global accesses — while the next tile's MMAs run.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -150,10 +151,13 @@ struct Epilogue {
   int vec_ok;              // every row pointer (C, residual, out2, addend) is 16-byte aligned: float4 accesses allowed
   int col_vec;             // col_scale / col_shift are 16-byte aligned: float4 broadcast loads allowed
   int tma_store;           // C (and out2) leave through TMA stores from a swizzled shared-memory tile (needs vec_ok)
+  const float* post_res;   // [M, ld_post] or null: added AFTER the activation, followed by post_act (a block's shortcut)
+  int ld_post;
+  int post_act;            // 0 none, 1 relu, 2 leaky relu (same slope)
 };
 
 // TMEM accumulators per tile: NUM_HI for the hi*hi products (round-robin over k-steps) + 1 for the cross terms.
-template <int BLOCK_N, int NUM_HI, int STAGES>
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
 struct SmemLayout {
   static constexpr int kNumAcc = NUM_HI + 1;
   static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
@@ -164,7 +168,7 @@ struct SmemLayout {
   static constexpr uint32_t kEpiBytes = kStoreBytes;
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
-  static constexpr uint32_t kTmemCols = 2 * kNumAcc * BLOCK_N;  // double-buffered accumulators
+  static constexpr uint32_t kTmemCols = ACC_BUFS * kNumAcc * BLOCK_N;  // ACC_BUFS = 2: double-buffered accumulators
   static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
 };
 
@@ -177,14 +181,16 @@ struct SmemLayout {
 // with the number of accumulation steps (measured 3e-5 relative at K = 3840 with a single accumulator).  The
 // (2^-11 smaller) cross terms therefore get their own accumulator, and for long K the hi*hi products of
 // consecutive k-steps rotate over three accumulators; the epilogue adds them in fp32 round-to-nearest.
-template <int BLOCK_N, int NUM_HI, int STAGES>
+// ACC_BUFS = 1 (long reductions with wide tiles: 4 accumulators x 128 columns fill TMEM) trades the epilogue / mainloop
+// overlap — a few per cent of a K > 1024 mainloop — for 128-column MMAs, which halve the shared-memory reads of A per flop.
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
 __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo,
                                                           const __grid_constant__ CUtensorMap map_c,
                                                           const __grid_constant__ CUtensorMap map_o2, float* __restrict__ C,
                                                           int64_t M, int N, int K, int ldc, Epilogue ep) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>;
   constexpr int kNumAcc = L::kNumAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int64_t num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * num_n;
+  // tile indices fit 32 bits (the launcher checks): 64-bit divisions by num_n cost several hundred cycles per tile and role
+  const uint32_t num_tiles = (uint32_t)(((M + BLOCK_M - 1) / BLOCK_M) * num_n);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
       mbar_init(split_bar(s), 4);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < ACC_BUFS; ++b) {
       mbar_init(tmem_full_bar(b), 1);
       mbar_init(tmem_empty_bar(b), L::kEpiWarps);
     }
@@ -231,8 +238,9 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     // ---------------- TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (int)(tile / num_n) * BLOCK_M, n0 = (int)(tile % num_n) * BLOCK_N;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t m_blk = tile / (uint32_t)num_n;
+        const int m0 = (int)m_blk * BLOCK_M, n0 = (int)(tile - m_blk * (uint32_t)num_n) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = (int)(it % STAGES);
           mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
@@ -249,9 +257,9 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     if (lane == 0) {
       const uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
       uint32_t it = 0, lt = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u;
-        mbar_wait(tmem_empty_bar(buf), ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator set
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt % ACC_BUFS;
+        mbar_wait(tmem_empty_bar(buf), ((lt / ACC_BUFS) & 1u) ^ 1u);  // epilogue has drained this accumulator set
         tcgen05_fence_after();
         const uint32_t acc0 = tmem_base + buf * (kNumAcc * BLOCK_N);
         const uint32_t acc_x = acc0 + (uint32_t)NUM_HI * BLOCK_N;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     // ---------------- splitters (warps 2..5)
     const int t = threadIdx.x - 64;  // 0..127
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = (int)(it % STAGES);
         mbar_wait(full_bar(s), (it / STAGES) & 1u);
@@ -314,26 +322,57 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     const uint32_t stg = base + L::kTileBytes + (uint32_t)ew * 4096u;
     const bool vec_ok = ep.vec_ok != 0;
     const bool tma_out = ep.tma_store != 0;
-    const bool col_vec = ep.col_vec != 0;
     if (tma_out && lane == 0) {
       tma_prefetch_desc(&map_c);
       if (ep.out2) tma_prefetch_desc(&map_o2);
     }
+    // The side inputs of the epilogue (residual, addend, post-residual rows) are requested into L2 one tile ahead:
+    // their DRAM latency would otherwise sit in the epilogue's critical path, once per 32-column chunk.
+    const bool side_inputs = ep.residual || ep.out2 || ep.post_res;
+    auto prefetch_side = [&](uint32_t tile_p) {
+      const uint32_t mb = tile_p / (uint32_t)num_n;
+      const int64_t mp = (int64_t)mb * BLOCK_M + 32 * q + lane;
+      const int np0 = (int)(tile_p - mb * (uint32_t)num_n) * BLOCK_N;
+      if (mp >= M) return;
+      for (int c0 = 32 * half; c0 < BLOCK_N && np0 + c0 < N; c0 += kChunkStep) {
+        if (ep.residual) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + mp * (int64_t)ep.ld_res + np0 + c0));
+        if (ep.out2) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.addend + mp * (int64_t)ep.ld_add + np0 + c0));
+        if (ep.post_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.post_res + mp * (int64_t)ep.ld_post + np0 + c0));
+      }
+    };
+    if (side_inputs && blockIdx.x < num_tiles) prefetch_side(blockIdx.x);
     uint32_t lt = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int64_t m = (tile / num_n) * BLOCK_M + 32 * q + lane;
-      const int n0 = (int)(tile % num_n) * BLOCK_N;
-      const uint32_t buf = lt & 1u;
+    constexpr int kChunksPerWarp = BLOCK_N / kChunkStep;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t m_blk = tile / (uint32_t)num_n;
+      const int row0 = (int)m_blk * BLOCK_M + 32 * q;
+      const int64_t m = (int64_t)row0 + lane;
+      const int n0 = (int)(tile - m_blk * (uint32_t)num_n) * BLOCK_N;
+      const uint32_t buf = lt % ACC_BUFS;
       const float rs = (ep.row_scale && m < M) ? ep.row_scale[m] : 1.0f;
-      mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1u);
+      // column scale / shift of this warp's chunks: lane j fetches column j's pair now (one coalesced load, in flight while
+      // the accumulators are awaited); the values reach the other lanes by shuffle.  (Eight broadcast float4 loads per
+      // chunk, issued after the TMEM read, were the longest stall of the epilogue: with 227 KB of the SM given to shared
+      // memory they miss L1.)
+      float cs_pre[kChunksPerWarp], cb_pre[kChunksPerWarp];
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int n = n0 + 32 * half + kChunkStep * ci + lane;
+        cs_pre[ci] = (ep.col_scale && n < N) ? __ldg(ep.col_scale + n) : 1.0f;
+        cb_pre[ci] = (ep.col_shift && n < N) ? __ldg(ep.col_shift + n) : 0.0f;
+      }
+      if (side_inputs && tile + gridDim.x < num_tiles) prefetch_side(tile + gridDim.x);
+      mbar_wait(tmem_full_bar(buf), (lt / ACC_BUFS) & 1u);
       tcgen05_fence_after();
       const uint32_t acc0 = tmem_base + buf * (kNumAcc * BLOCK_N) + ((uint32_t)(32 * q) << 16);
       float* __restrict__ crow = C + m * (int64_t)ldc;
       const float* __restrict__ rrow = ep.residual ? ep.residual + m * (int64_t)ep.ld_res : nullptr;
       float* __restrict__ orow = ep.out2 ? ep.out2 + m * (int64_t)ep.ld2 : nullptr;
       const float* __restrict__ arow = ep.out2 ? ep.addend + m * (int64_t)ep.ld_add : nullptr;
-#pragma unroll 1
-      for (int c0 = 32 * half; c0 < BLOCK_N; c0 += kChunkStep) {
+      const float* __restrict__ prow = ep.post_res ? ep.post_res + m * (int64_t)ep.ld_post : nullptr;
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int c0 = 32 * half + kChunkStep * ci;
         float sum[32];
         {
           // the accumulators of this chunk: issue the TMEM loads pairwise, one wait per pair
@@ -358,23 +397,11 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
         }
         if (ep.col_scale) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (col_vec && n + 3 < N) s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + n));
-            else { if (n < N) s4.x = ep.col_scale[n]; if (n + 1 < N) s4.y = ep.col_scale[n + 1]; if (n + 2 < N) s4.z = ep.col_scale[n + 2]; if (n + 3 < N) s4.w = ep.col_scale[n + 3]; }
-            sum[j] *= s4.x; sum[j + 1] *= s4.y; sum[j + 2] *= s4.z; sum[j + 3] *= s4.w;
-          }
+          for (int j = 0; j < 32; ++j) sum[j] *= __shfl_sync(0xffffffffu, cs_pre[ci], j);
         }
         if (ep.col_shift) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_vec && n + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(ep.col_shift + n));
-            else { if (n < N) b4.x = ep.col_shift[n]; if (n + 1 < N) b4.y = ep.col_shift[n + 1]; if (n + 2 < N) b4.z = ep.col_shift[n + 2]; if (n + 3 < N) b4.w = ep.col_shift[n + 3]; }
-            sum[j] += b4.x; sum[j + 1] += b4.y; sum[j + 2] += b4.z; sum[j + 3] += b4.w;
-          }
+          for (int j = 0; j < 32; ++j) sum[j] += __shfl_sync(0xffffffffu, cb_pre[ci], j);
         }
         if (c0 + kChunkStep >= BLOCK_N) {
           // this warp's TMEM reads of the tile are done: hand the accumulator set back to the MMA warp
@@ -383,59 +410,54 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
         }
         if (tma_out) {
-          // values -> swizzled 32 x 32 tile in shared memory -> one TMA store per warp (clipped at M and N)
-          float4 aa[8];
-          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading this warp's tile
-          __syncwarp();
+          // values -> swizzled 32 x 32 tile in shared memory -> one TMA store per warp (clipped at M and N).
+          // Every run-time condition is tested once per chunk, outside the loops over the 32 columns, and the loads of a
+          // side input are issued together: a branchy per-column body made the epilogue the slowest role of short-K layers.
+          const bool row_ok = m < M;
+          const bool full_chunk = n0 + c0 + 32 <= N;
+          const int nc = n0 + c0;
+          // sum[] += side[row, nc .. nc + 31]
+          auto add_row = [&](const float* __restrict__ side_row) {
+            if (row_ok && full_chunk) {
+              float4 t4[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            float v[4];
+              for (int j = 0; j < 8; ++j) t4[j] = *reinterpret_cast<const float4*>(side_row + nc + 4 * j);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = sum[j + e];
-            const bool in4 = (m < M) && (n + 3 < N);
-            if (rrow) {
-              if (in4) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
-                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-              } else if (m < M) {
+              for (int j = 0; j < 8; ++j) { sum[4 * j] += t4[j].x; sum[4 * j + 1] += t4[j].y; sum[4 * j + 2] += t4[j].z; sum[4 * j + 3] += t4[j].w; }
+            } else if (row_ok) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (n + e < N) v[e] += rrow[n + e];
-              }
+              for (int e = 0; e < 32; ++e) if (nc + e < N) sum[e] += side_row[nc + e];
             }
-            if (ep.act == 1) {
+          };
+          auto activate_all = [&](int act) {
+            if (act == 1) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-            } else if (ep.act == 2) {
+              for (int e = 0; e < 32; ++e) sum[e] = fmaxf(sum[e], 0.f);
+            } else if (act == 2) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * ep.slope;
+              for (int e = 0; e < 32; ++e) sum[e] = sum[e] > 0.f ? sum[e] : sum[e] * ep.slope;
             }
-            *reinterpret_cast<float4*>(stg_ptr + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-            if (orow) {
-              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (in4) a4 = *reinterpret_cast<const float4*>(arow + n);
-              else if (m < M) {
-                if (n < N) a4.x = arow[n];
-                if (n + 1 < N) a4.y = arow[n + 1];
-                if (n + 2 < N) a4.z = arow[n + 2];
-                if (n + 3 < N) a4.w = arow[n + 3];
-              }
-              aa[j >> 2] = make_float4(v[0] + a4.x, v[1] + a4.y, v[2] + a4.z, v[3] + a4.w);
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          const int row0 = (int)((tile / num_n) * BLOCK_M) + 32 * q;
-          if (lane == 0) tma_store_2d(&map_c, stg, n0 + c0, row0);
-          if (orow) {
-            if (lane == 0) tma_store_wait_read();
+          };
+          auto stage_and_store = [&](const CUtensorMap* map) {
+            if (lane == 0) tma_store_wait_read();  // the previous store has finished reading this warp's tile
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(stg_ptr + lane * 128 + ((c ^ (lane & 7)) << 4)) = aa[c];
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg_ptr + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) tma_store_2d(&map_o2, stg, n0 + c0, row0);
+            if (lane == 0) tma_store_2d(map, stg, nc, row0);
+          };
+          if (rrow) add_row(rrow);
+          activate_all(ep.act);
+          if (prow) {
+            add_row(prow);
+            activate_all(ep.post_act);
+          }
+          stage_and_store(&map_c);
+          if (orow) {
+            add_row(arow);
+            stage_and_store(&map_o2);
           }
         } else if (m < M) {
 #pragma unroll
@@ -461,6 +483,22 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
             } else if (ep.act == 2) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * ep.slope;
+            }
+            if (prow) {
+              if (full4) {
+                const float4 pp = *reinterpret_cast<const float4*>(prow + n);
+                v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < N) v[e] += prow[n + e];
+              }
+              if (ep.post_act == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              } else if (ep.post_act == 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * ep.slope;
+              }
             }
             if (full4) {
               *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
@@ -543,18 +581,19 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t
   return KPREG_OK;
 }
 
-template <int BLOCK_N, int NUM_HI, int STAGES>
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
 int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
                        const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>;
   static bool configured = false;
   if (!configured) {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     configured = true;
   }
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
+  if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -589,14 +628,18 @@ int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int tran
 // C[m, n] (row pitch ldc) = epilogue(A[m, kd] (row pitch lda) * Bt^T) with pre-split weights.
 int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
                    const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
-                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, cudaStream_t stream) {
+                   int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
+                   int post_act, cudaStream_t stream) {
   if (!gemm_tc_supported(m, kd, n, lda, a)) return KPREG_E_INVALID;
   const int ldb = ldb_for(kd);
   const float* hi = w_split;
   const float* lo = w_split + (size_t)npad_for(n) * ldb;
   // long reductions rotate the hi*hi products over three accumulators (see the accuracy note above)
   const int num_hi = kd > 1024 ? 3 : 1;
-  const int block_n = n <= 32 ? 32 : ((n <= 64 || num_hi == 3) ? 64 : 128);
+  // wide outputs of long reductions: 128-column tiles with single-buffered accumulators (4 x 128 TMEM columns)
+  static const bool no_wide3 = [] { const char* e = getenv("KPREG_GEMM_NO_WIDE3"); return e && e[0] == '1'; }();
+  const bool wide3 = num_hi == 3 && n > 64 && !no_wide3;
+  const int block_n = n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128);
   CUtensorMap ma, mbh, mbl;
   int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
   if (rc) return rc;
@@ -605,8 +648,9 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   rc = make_map(&mbl, lo, n, kd, ldb, block_n);
   if (rc) return rc;
   auto aligned = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0); };
-  const int vec_ok = aligned(c, ldc) && aligned(residual, ld_res) && aligned(out2, ld2) && aligned(addend, ld_add);
+  const int vec_ok = aligned(c, ldc) && aligned(residual, ld_res) && aligned(out2, ld2) && aligned(addend, ld_add) && aligned(post_res, ld_post);
   // outputs leave through TMA when every pointer / pitch is 16-byte aligned (the store clips at M and N itself)
+  // (a staged tile flushed with coalesced STG.128 instead of the TMA store was measured 20-40 % slower on short-K layers)
   const int tma_store = vec_ok;
   CUtensorMap mc, mo2;
   rc = make_map(&mc, tma_store ? c : nullptr, m, n, ldc, 32);
@@ -614,14 +658,16 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   rc = make_map(&mo2, (tma_store && out2) ? out2 : nullptr, m, n, ld2, 32);
   if (rc) return rc;
   const int col_vec = ((reinterpret_cast<uintptr_t>(col_scale) | reinterpret_cast<uintptr_t>(col_shift)) & 15) == 0;
-  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, col_vec, tma_store};
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, col_vec, tma_store,
+              post_res, ld_post, post_act};
   if (num_hi == 3) {
-    if (block_n == 32) return launch_tile_config<32, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    return launch_tile_config<64, 3, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 32) return launch_tile_config<32, 3, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 64) return launch_tile_config<64, 3, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 3, 3, 1>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
   }
-  if (block_n == 32) return launch_tile_config<32, 1, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  if (block_n == 64) return launch_tile_config<64, 1, 4>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  return launch_tile_config<128, 1, 3>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 32) return launch_tile_config<32, 1, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 1, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 1, 3, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
 }
 
 }  // namespace kpreg

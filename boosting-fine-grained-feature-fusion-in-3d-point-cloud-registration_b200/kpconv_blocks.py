@@ -320,6 +320,9 @@ class ResnetBottleneckBlock(nn.Module):
 
         x = self.unary1(features, lens_pre) if isinstance(self.unary1, UnaryBlock) else features
         x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)
+        if _fused(x) and not isinstance(self.unary_shortcut, UnaryBlock):
+            # identity shortcut: leaky_relu(res2net(x) + shortcut) rides on res2net's last GEMM
+            return self.res2net(x, max_pool(features, inds, order) if strided else features)
         x = self.res2net(x)
         if not _fused(x):
             # my_Bottle2neck ends in a ReLU, so this LeakyReLU is the identity; kept on the autograd path only so

@@ -297,9 +297,10 @@ def _rows(t: torch.Tensor, name: str):
 
 
 def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act=None, slope: float = 0.1, out=None,
-                   out2=None, addend=None, gemm: int = 1):
+                   out2=None, addend=None, gemm: int = 1, post_residual=None, post_act=None):
     """act((x @ weight.T) * col_scale + col_shift + residual) -> out [M,N] (kpreg_linear_forward).
-    ``out`` may be a column slice of a wider buffer; ``out2`` (optional) receives out + addend."""
+    ``out`` may be a column slice of a wider buffer; ``out2`` (optional) receives out + addend;
+    ``post_residual`` (optional) is added after ``act`` and followed by ``post_act``."""
     lib = _lib.load()
     x, ldx = _rows(x, "x")
     m, k = x.shape
@@ -324,14 +325,19 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     if out2 is not None:
         addend, ld_add = _rows(addend, "addend")
         o2_ptr, ld2, add_ptr = out2.data_ptr(), int(out2.stride(0)), addend.data_ptr()
+    post_ptr, ld_post = None, 0
+    if post_residual is not None:
+        post_residual, ld_post = _rows(post_residual, "post_residual")
+        post_ptr = post_residual.data_ptr()
     cs = None if col_scale is None else _f32c(col_scale, "col_scale")
     cb = None if col_shift is None else _f32c(col_shift, "col_shift")
     nbytes = _lib.size_query("kpreg_linear_workspace_bytes", k, n)
     ws = _lib.workspaces.get(nbytes, dev)
     w_ptr = presplit.buf.data_ptr() if presplit is not None else weight.data_ptr()
     rc = lib.kpreg_linear_forward(x.data_ptr(), ldx, w_ptr, m, k, n, _lib.ptr(cs), _lib.ptr(cb), res_ptr, ld_res,
-                                  ACT[act], float(slope), out.data_ptr(), ldc, o2_ptr, ld2, add_ptr, ld_add,
-                                  2 if presplit is not None else int(gemm), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+                                  ACT[act], float(slope), out.data_ptr(), ldc, o2_ptr, ld2, add_ptr, ld_add, post_ptr, ld_post,
+                                  ACT[post_act], 2 if presplit is not None else int(gemm), ws.data_ptr(), ws.numel(),
+                                  _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_linear_forward")
     return out
 

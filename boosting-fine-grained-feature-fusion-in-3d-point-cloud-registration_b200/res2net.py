@@ -64,10 +64,12 @@ class my_Bottle2neck(nn.Module):
             self._kpreg_chain = cache
         return cache[1]
 
-    def _fused_forward(self, x):
+    def _fused_forward(self, x, shortcut=None):
         """Inference on CUDA: every Linear + eval-BatchNorm (+ ReLU) is one tensor-core GEMM with a fused
-        epilogue; each chained layer also emits `its output + the next group` (the next layer's input); the
-        residual projection is folded into the last GEMM by concatenating its input and weights along K."""
+        epilogue; the chained layers run in one register-resident kernel where the width allows it (otherwise
+        each emits `its output + the next group`, the next layer's input); the residual projection is folded
+        into the last GEMM by concatenating its input and weights along K; ``shortcut`` (the enclosing block's
+        identity shortcut) makes that GEMM return leaky_relu(unit output + shortcut, 0.1)."""
         from . import kpconv_blocks as kb
         from . import ops
         w, n_groups = self.width, self.scale
@@ -104,19 +106,23 @@ class my_Bottle2neck(nn.Module):
             if cache is None or cache[0] != key:
                 cache = (key, torch.cat([w3, wd], 1).contiguous(), (b3 + bd).contiguous())
                 self._kpreg_joint = cache
-            return ops.linear_forward(z, cache[1], None, cache[2], act="relu", gemm=gemm)
+            return ops.linear_forward(z, cache[1], None, cache[2], act="relu", gemm=gemm, post_residual=shortcut,
+                                      post_act="leaky_relu" if shortcut is not None else None)
         residual = x
         if self.downsample is not None:
             wd, bd = _folded(self.downsample[0], self.downsample[1])
             residual = ops.linear_forward(x, wd, None, bd, gemm=gemm)
-        return ops.linear_forward(z[:, :k_cat], w3, None, b3, residual=residual, act="relu", gemm=gemm)
+        return ops.linear_forward(z[:, :k_cat], w3, None, b3, residual=residual, act="relu", gemm=gemm, post_residual=shortcut,
+                                  post_act="leaky_relu" if shortcut is not None else None)
 
-    def forward(self, x):
+    def forward(self, x, shortcut=None):
+        """``shortcut`` (optional, not in the reference): returns leaky_relu(unit(x) + shortcut, 0.1), the tail of
+        ResnetBottleneckBlock.forward, fused into the last GEMM on the inference path."""
         if (not self.training and x.is_cuda and not torch.is_grad_enabled() and self.stype == 'normal'
                 and self.scale > 1 and self.width % 4 == 0):
             from . import kpconv_blocks as kb
             if kb.FUSED_GLUE:
-                return self._fused_forward(x)
+                return self._fused_forward(x, shortcut)
         groups = torch.split(self.relu(self.bn1(self.conv1(x))), self.width, 1)
         outs, carry = [], None
         for i in range(self.nums):
@@ -127,7 +133,8 @@ class my_Bottle2neck(nn.Module):
             outs.append(groups[self.nums] if self.stype == 'normal' else self.pool(groups[self.nums]))
         out = self.bn3(self.conv3(torch.cat(outs, 1)))
         residual = x if self.downsample is None else self.downsample(x)
-        return self.relu(out + residual)
+        out = self.relu(out + residual)
+        return out if shortcut is None else torch.nn.functional.leaky_relu(out + shortcut, 0.1)
 
 
 class my_res2Net(nn.Module):
@@ -146,5 +153,5 @@ class my_res2Net(nn.Module):
         self.layer1 = nn.Sequential(block(self.inplanes, out_dim, 1, downsample=downsample, stype='normal',
                                           baseWidth=baseWidth, scale=scale))
 
-    def forward(self, x):
-        return self.layer1(x)
+    def forward(self, x, shortcut=None):
+        return self.layer1(x) if shortcut is None else self.layer1[0](x, shortcut)

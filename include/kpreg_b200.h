@@ -173,6 +173,9 @@ KPREG_API int kpreg_kabsch(const float* a, const float* b, float* w, const int64
  *   col_scale / col_shift and the following ReLU in `act` (0 none, 1 relu, 2 leaky relu with `slope`).
  *   x [M, ldx], weight [N, K] (nn.Linear layout), out [M, ldc]; col_scale / col_shift / residual may be NULL.
  *   out2 (optional) [M, ld2] receives out + addend[M, ld_add] — the input of the next layer of res2net's chain.
+ *   post_residual (optional) [M, ld_post] is added AFTER `act` and followed by `post_act`:
+ *   out = post_act(act(...) + post_residual) — ResnetBottleneckBlock's `leaky_relu(res2net(x) + shortcut)`
+ *   (finegrained_kpconv_blocks.py:723-725) riding on res2net's last GEMM.
  *   gemm: 1 = tcgen05 3xTF32 (falls back when the shape is not TMA-addressable), 0 = fp32 CUDA cores.
  *
  * kpreg_segment_norm_forward: out = act( (x - mean[c]) * rstd[c] + residual ), statistics per cloud c and channel
@@ -193,7 +196,8 @@ KPREG_API int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes);
 KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
                                    const float* col_scale, const float* col_shift, const float* residual, int ld_res,
                                    int act, float slope, float* out, int ldc, float* out2, int ld2, const float* addend,
-                                   int ld_add, int gemm, void* workspace, size_t workspace_bytes, void* stream);
+                                   int ld_add, const float* post_residual, int ld_post, int post_act, int gemm,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 KPREG_API int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes);
 KPREG_API int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
                                          int channels, float eps, const float* residual, int ld_res, int act, float slope,

@@ -50,7 +50,7 @@ def test_tc_contraction_many_row_tiles(oracle):
 
 
 @pytest.mark.parametrize("m,k,n", [(5000, 32, 128), (1000, 28, 28), (777, 224, 224), (4096, 128, 32), (130, 1024, 256), (300, 3, 16),
-                                   (513, 40, 30), (64, 96, 72), (2000, 1100, 40)])
+                                   (513, 40, 30), (64, 96, 72), (2000, 1100, 40), (300, 1100, 200), (1000, 2048, 130)])
 @pytest.mark.parametrize("gemm", [1, 0])
 def test_linear_forward_matches_torch(m, k, n, gemm):
     """nn.Linear(bias=False) + folded BatchNorm + residual + activation (+ the chained second output)."""
@@ -154,3 +154,33 @@ def test_bottleneck_fused_chain_matches_stock_layers():
             kpconv_blocks.CHAIN_KERNEL = True
     assert rel_err(chain.cpu().numpy(), stock.cpu().numpy()) < 1e-5
     assert rel_err(layers.cpu().numpy(), stock.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("m,k,n", [(3000, 256, 128), (517, 60, 28), (200, 1100, 72)])
+@pytest.mark.parametrize("gemm", [1, 0])
+def test_linear_post_residual(m, k, n, gemm):
+    """out = leaky_relu(relu(x W^T + shift) + shortcut): a block's identity shortcut riding on res2net's last GEMM."""
+    torch.manual_seed(m + n)
+    x, w = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda") / k ** 0.5
+    shift, short = torch.randn(n, device="cuda"), torch.randn(m, n, device="cuda")
+    got = ops.linear_forward(x, w, None, shift, act="relu", post_residual=short, post_act="leaky_relu", gemm=gemm)
+    want = torch.nn.functional.leaky_relu(torch.relu(x.double() @ w.double().t() + shift.double()) + short.double(), 0.1)
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+def test_res2net_unit_with_fused_shortcut():
+    from kpreg_b200 import kpconv_blocks
+    from kpreg_b200.res2net import my_Bottle2neck, my_res2Net
+    torch.manual_seed(4)
+    net = my_res2Net(my_Bottle2neck, 64, 256, baseWidth=14, scale=8).cuda().eval()
+    x, short = torch.randn(2111, 64, device="cuda"), torch.randn(2111, 256, device="cuda")
+    with torch.no_grad():
+        fused = net(x, short)
+        kpconv_blocks.FUSED_GLUE = False
+        try:
+            stock = torch.nn.functional.leaky_relu(net(x) + short, 0.1)
+            stock2 = net(x, short)
+        finally:
+            kpconv_blocks.FUSED_GLUE = True
+    assert rel_err(fused.cpu().numpy(), stock.cpu().numpy()) < 1e-5
+    assert torch.equal(stock, stock2)

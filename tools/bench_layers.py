@@ -62,6 +62,13 @@ def d_pool(_res, x, idx, *a, **kw):
     return f"Nq={nq} H={h} C={x.shape[1]}", 4 * nq * h + 4 * x.shape[0] * x.shape[1] + 4 * nq * x.shape[1]
 
 
+def d_chain(_res, t, pack, z, x_copy=None):
+    m = t.shape[0]
+    g = (pack.n_layers + 1) * pack.width
+    return f"M={m} w={pack.width} L={pack.n_layers}", 4 * m * (2 * g + (2 * x_copy.shape[1] if x_copy is not None else 0))
+
+
+ops.chain_forward = wrap("chain", ops.chain_forward, d_chain)
 ops.linear_forward = wrap("linear", ops.linear_forward, d_linear)
 ops.segment_norm = wrap("segnorm", ops.segment_norm, d_norm)
 ops.kpconv_forward = wrap("kpconv", ops.kpconv_forward, d_kpconv)
