@@ -103,6 +103,10 @@ def kpconv_work(meta, cfg):
     out_dim, in_dim, layer = cfg.first_feats_dim, cfg.in_feats_dim, 0
     gather_bytes = contract_flops = gather_flops = linear_bytes = linear_flops = norm_bytes = 0
 
+    def chain_ok(width, n_layers):
+        from kpreg_b200 import kpconv_blocks, ops
+        return kpconv_blocks.CHAIN_KERNEL and kpconv_blocks.FUSED_GLUE and ops.chain_supported(width, n_layers)
+
     def lin(m, k_in, n_out):
         nonlocal linear_bytes, linear_flops
         linear_bytes += 4 * m * (k_in + n_out) + 4 * k_in * n_out
@@ -130,13 +134,20 @@ def kpconv_work(meta, cfg):
                 norm_bytes += 8 * n_s * mid
             norm_bytes += 8 * n_q * mid
             lin(n_q, mid, 8 * wid)
-            for _ in range(7):
-                lin(n_q, wid, wid)
-            lin(n_q, mid, out_dim)
-            lin(n_q, 8 * wid, out_dim)
+            if chain_ok(wid, 7):
+                # the seven chained layers in one kernel: t read once, the concatenation (+ the copy of the block input) written once
+                linear_bytes += 4 * n_q * (2 * 8 * wid + 2 * mid) + 7 * 4 * wid * wid
+                linear_flops += 7 * 2 * n_q * wid * wid
+            else:
+                for _ in range(7):
+                    lin(n_q, wid, wid)
+            # conv3 and the residual projection as one GEMM over the K-concatenation [cat | x]
+            lin(n_q, 8 * wid + mid, out_dim)
             if in_dim != out_dim:
                 lin(n_q, in_dim, out_dim)
                 norm_bytes += 12 * n_q * out_dim
+            else:
+                linear_bytes += 4 * n_q * out_dim  # identity shortcut read by conv3's epilogue
         in_dim = out_dim // 2 if name.startswith("simple") else out_dim
         if strided:
             layer += 1
@@ -359,7 +370,7 @@ def main():
                   "linear": work["linear_bytes"], "kpconv_contract": None}[top]
         names = {"kpconv_gather": "k_kpconv_gather (KPConv gather + influence + aggregation)",
                  "grid_query": "k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
-                 "linear": "k_gemm_tc (block Linear layers, tcgen05 3xTF32)",
+                 "linear": "k_gemm_tc + k_chain (block Linear layers: tcgen05 3xTF32 GEMMs, register-resident res2net chain)",
                  "kpconv_contract": "k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 3xTF32)"}
         if top == "kpconv_contract":
             ach = work["contract_flops"] / (fam_ms[top] * 1e-3) / 1e12
@@ -379,18 +390,19 @@ def main():
             "grid_query_GBs": work["query_bytes"] / max(fam_ms["grid_query"], 1e-9) / 1e6,
             "segment_norm_GBs": work["segment_norm_bytes"] / max(fam_ms["segment_norm"], 1e-9) / 1e6,
         }
-        # DRAM traffic of the family from the committed ncu capture (profiles/r1d_dram_traffic.json: dram__bytes_read.sum +
-        # dram__bytes_write.sum over one step's launches at 8 pairs), scaled to this run's pairs per step
-        tpath = os.path.join(ROOT, "profiles", "r1d_dram_traffic.json")
-        fam_kernel = {"linear": "k_gemm_tc", "kpconv_contract": "k_gemm_tc", "kpconv_gather": "k_kpconv_gather_mma",
-                      "grid_query": "k_grid_query"}.get(top)
-        if os.path.exists(tpath) and fam_kernel:
+        # DRAM traffic of the family from the committed ncu capture (profiles/r1g_dram_traffic.json: dram__bytes_read.sum +
+        # dram__bytes_write.sum over one step's launches), scaled to this run's pairs per step
+        tpath = os.path.join(ROOT, "profiles", "r1g_dram_traffic.json")
+        fam_kernels = {"linear": ("k_gemm_tc", "k_chain"), "kpconv_contract": ("k_gemm_tc",),
+                       "kpconv_gather": ("k_kpconv_gather_mma", "k_kpconv_c1"), "grid_query": ("k_grid_query",)}.get(top)
+        if os.path.exists(tpath) and fam_kernels:
             tr = json.load(open(tpath))
-            f = tr["families"].get(fam_kernel)
-            if f:
-                roof["traffic"] = (f["dram_read_MB"] + f["dram_write_MB"]) * 1e6 * args.pairs / tr["pairs"]
-                roof["traffic_note"] = (f"bytes per step, all {fam_kernel} launches (ncu capture at {tr['pairs']} pairs/step scaled to "
-                                        f"{args.pairs}); achieved / algorithmic figures are per step as well")
+            fs = [tr["families"][k] for k in fam_kernels if k in tr["families"]]
+            if fs:
+                roof["traffic"] = sum(f["dram_read_MB"] + f["dram_write_MB"] for f in fs) * 1e6 * args.pairs / tr["pairs"]
+                roof["traffic_note"] = (f"bytes per step, all {' + '.join(fam_kernels)} launches (ncu capture at {tr['pairs']} pairs/step "
+                                        f"scaled to {args.pairs}; k_gemm_tc also serves the KPConv contraction); achieved / algorithmic "
+                                        "figures are per step as well")
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}

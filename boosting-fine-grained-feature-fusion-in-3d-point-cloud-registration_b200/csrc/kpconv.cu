@@ -50,7 +50,17 @@ __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ 
   if (lane == 0) pos[row] = (float)acc > 0.0f ? 1 : 0;
 }
 
-// Influence of the K kernel points on one neighbour (relative position rx,ry,rz).
+// rsqrt.approx.ftz: the argument is clamped to >= 1e-30 (a normal number) by every caller, so the denormal pre-scaling
+// that rsqrtf() compiles to (a compare and two conditional multiplies per call) can never trigger.
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Influence of the K kernel points on one neighbour (relative position rx,ry,rz).  INFL >= 0 fixes the influence mode at
+// compile time (no per-kernel-point branches); INFL < 0 reads it from `influence`.
+template <int INFL = -1>
 __device__ __forceinline__ void influences(float rx, float ry, float rz, const float* __restrict__ s_kp, int n_kpts,
                                            float extent, int influence, int aggregation, float* __restrict__ w_out) {
   const float inv_extent = 1.0f / extent;
@@ -62,8 +72,9 @@ __device__ __forceinline__ void influences(float rx, float ry, float rz, const f
     if (k < n_kpts) {
       const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
       const float d2 = dx * dx + dy * dy + dz * dz;
-      if (influence == 1) w = fmaxf(1.0f - d2 * rsqrtf(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
-      else if (influence == 2) { const float sig = extent * 0.3f; w = expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
+      const int mode = INFL >= 0 ? INFL : influence;
+      if (mode == 1) w = fmaxf(1.0f - d2 * rsqrt_fast(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
+      else if (mode == 2) { const float sig = extent * 0.3f; w = expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
       else w = 1.0f;
       if (d2 < best) { best = d2; best_k = k; }
     }
@@ -181,13 +192,15 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                  "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
+template <int INFL = -1>
 __device__ __forceinline__ float influence_one(float rx, float ry, float rz, float kx, float ky, float kz, float inv_extent,
                                                float extent, int influence, float& d2_out) {
   const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
   const float d2 = dx * dx + dy * dy + dz * dz;
   d2_out = d2;
-  if (influence == 1) return fmaxf(1.0f - d2 * rsqrtf(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
-  if (influence == 2) { const float sig = extent * 0.3f; return expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
+  const int mode = INFL >= 0 ? INFL : influence;
+  if (mode == 1) return fmaxf(1.0f - d2 * rsqrt_fast(fmaxf(d2, 1e-30f)) * inv_extent, 0.0f);
+  if (mode == 2) { const float sig = extent * 0.3f; return expf(-d2 / (2.0f * sig * sig + 1e-9f)); }
   return 1.0f;
 }
 
@@ -197,8 +210,12 @@ __device__ __forceinline__ float influence_one(float rx, float ry, float rz, flo
 // its D fragment covers the 2 * NT contiguous channels [2t * NT, 2t * NT + 2 NT) of rows g and g + 8 (float4 stores).
 // The index row of the next query is requested before the current query's work.  (Requesting the feature rows of k-step
 // s + 1 before the MMAs of k-step s was measured SLOWER on B200 — 5-9 % — through the registers it costs.)
-template <typename IdxT, int NT, bool VEC>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
-__global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
+// INFL: 1 = the 'linear' influence of every shipped config fixed at compile time, -1 = mode read at run time.
+// resident CTAs per SM the register allocation must leave room for (the occupancies the kernel was tuned at)
+constexpr int gather_min_blocks(int nt) { return nt <= 4 ? 6 : (nt <= 8 ? 5 : (nt <= 16 ? 3 : 2)); }
+
+template <typename IdxT, int NT, bool VEC, int INFL>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
+__global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kpconv_gather_mma(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
     int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num,
@@ -269,10 +286,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
       const float bx = __shfl_sync(0xffffffffu, rb ? rx[1] : rx[0], hb & 31), by = __shfl_sync(0xffffffffu, rb ? ry[1] : ry[0], hb & 31),
                   bz = __shfl_sync(0xffffffffu, rb ? rz[1] : rz[0], hb & 31);
       float w[4], d2[4];
-      w[0] = influence_one(ax, ay, az, k0x, k0y, k0z, inv_extent, extent, influence, d2[0]);  // (k = g,     h = t)
-      w[1] = influence_one(ax, ay, az, k1x, k1y, k1z, inv_extent, extent, influence, d2[1]);  // (k = g + 8, h = t)
-      w[2] = influence_one(bx, by, bz, k0x, k0y, k0z, inv_extent, extent, influence, d2[2]);  // (k = g,     h = t + 4)
-      w[3] = influence_one(bx, by, bz, k1x, k1y, k1z, inv_extent, extent, influence, d2[3]);  // (k = g + 8, h = t + 4)
+      w[0] = influence_one<INFL>(ax, ay, az, k0x, k0y, k0z, inv_extent, extent, influence, d2[0]);  // (k = g,     h = t)
+      w[1] = influence_one<INFL>(ax, ay, az, k1x, k1y, k1z, inv_extent, extent, influence, d2[1]);  // (k = g + 8, h = t)
+      w[2] = influence_one<INFL>(bx, by, bz, k0x, k0y, k0z, inv_extent, extent, influence, d2[2]);  // (k = g,     h = t + 4)
+      w[3] = influence_one<INFL>(bx, by, bz, k1x, k1y, k1z, inv_extent, extent, influence, d2[3]);  // (k = g + 8, h = t + 4)
       if (!k0_ok) { w[0] = w[2] = 0.f; d2[0] = d2[2] = 3.4e38f; }
       if (!k1_ok) { w[1] = w[3] = 0.f; d2[1] = d2[3] = 3.4e38f; }
       if (!va) w[0] = w[1] = 0.f;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_gather_mma(
 // operator is one kernel: a lane per neighbour evaluates the K influences (fp32 FFMA), a transposing butterfly leaves
 // the total of kernel point k in lanes 2k / 2k+1 (16 shuffles), and every lane finishes c_out / 32 output channels
 // from register-resident weights.  No aggregate, no row predicate pass (sum_c x > 0 is x > 0) and no GEMM launch.
-template <typename IdxT, int CPL>  // CPL = output channels per lane (c_out <= 32 * CPL)
+template <typename IdxT, int CPL, int INFL>  // CPL = output channels per lane (c_out <= 32 * CPL); INFL as in k_kpconv_gather_mma
 __global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const float* __restrict__ kernel_points, const float* __restrict__ weights, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1(
     for (int k = 0; k < KMAX; ++k) v[k] = 0.f;
     if (va) {
       float w[KMAX];
-      influences(ax, ay, az, s_kp, n_kpts, extent, influence, aggregation, w);
+      influences<INFL>(ax, ay, az, s_kp, n_kpts, extent, influence, aggregation, w);
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) v[k] = w[k] * xa;
     }
@@ -441,14 +458,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1(
       for (int kk = 0; kk < 4; ++kk) {
         const int k = q4 + kk;
         float d2;
-        const float w = influence_one(bx, by, bz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_extent, extent, influence, d2);
+        const float w = influence_one<INFL>(bx, by, bz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_extent, extent, influence, d2);
         u[kk] = (vb && k < n_kpts) ? w * xb : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) v[k] += ((k & ~3) == q4) ? u[k & 3] : 0.f;
     } else if (vb) {
       float w[KMAX];
-      influences(bx, by, bz, s_kp, n_kpts, extent, influence, aggregation, w);
+      influences<INFL>(bx, by, bz, s_kp, n_kpts, extent, influence, aggregation, w);
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) v[k] = fmaf(w[k], xb, v[k]);
     }
@@ -690,10 +707,14 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   const IdxT* ip = static_cast<const IdxT*>(idx);
   ProfScope prof(KPREG_FAM_GATHER, stream);
   if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && n_s < ((int64_t)1 << 31) && g_gather_mma) {
-#define KP_GATHER_MMA(NT, VEC)                                                                                                 \
-  k_kpconv_gather_mma<IdxT, NT, VEC><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s,     \
-                                                                               n_nbrs, n_kpts, c_in, extent, influence,        \
-                                                                               aggregation, agg, inv_num, order)
+#define KP_GATHER_MMA_(NT, VEC, INFL)                                                                                          \
+  k_kpconv_gather_mma<IdxT, NT, VEC, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q,    \
+                                                                                     n_s, n_nbrs, n_kpts, c_in, extent,        \
+                                                                                     influence, aggregation, agg, inv_num, order)
+#define KP_GATHER_MMA(NT, VEC)                                                \
+  do {                                                                        \
+    if (influence == 1) KP_GATHER_MMA_(NT, VEC, 1); else KP_GATHER_MMA_(NT, VEC, -1); \
+  } while (0)
     // float4 path: whole rows of x and of the aggregate are 16-byte aligned
     const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
     if (c_in <= 8) KP_GATHER_MMA(1, false);
@@ -702,6 +723,7 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
     else if (c_in <= 64) { if (vec) KP_GATHER_MMA(8, true); else KP_GATHER_MMA(8, false); }
     else if (c_in <= 128) { if (vec) KP_GATHER_MMA(16, true); else KP_GATHER_MMA(16, false); }
     else { if (vec) KP_GATHER_MMA(32, true); else KP_GATHER_MMA(32, false); }
+#undef KP_GATHER_MMA_
 #undef KP_GATHER_MMA
     KP_LAUNCH_CHECK();
     return KPREG_OK;
@@ -789,12 +811,17 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
     int blocks = ceil_div(n_q, kGatherWarps);
     if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
     ProfScope prof(KPREG_FAM_GATHER, stream);
-#define KP_C1(IdxT, CPL)                                                                                                        \
-  k_kpconv_c1<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x, kernel_points, \
-                                                                   weights, n_q, n_s, n_nbrs, n_kpts, c_out, kp_extent, influence, \
-                                                                   aggregation, out, order)
+#define KP_C1_(IdxT, CPL, INFL)                                                                                                       \
+  k_kpconv_c1<IdxT, CPL, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x,               \
+                                                                         kernel_points, weights, n_q, n_s, n_nbrs, n_kpts, c_out,      \
+                                                                         kp_extent, influence, aggregation, out, order)
+#define KP_C1(IdxT, CPL)                                                       \
+  do {                                                                         \
+    if (influence == 1) KP_C1_(IdxT, CPL, 1); else KP_C1_(IdxT, CPL, -1);      \
+  } while (0)
     if (idx64) { if (c_out <= 32) KP_C1(int64_t, 1); else if (c_out <= 64) KP_C1(int64_t, 2); else KP_C1(int64_t, 4); }
     else { if (c_out <= 32) KP_C1(int32_t, 1); else if (c_out <= 64) KP_C1(int32_t, 2); else KP_C1(int32_t, 4); }
+#undef KP_C1_
 #undef KP_C1
     KP_LAUNCH_CHECK();
     return KPREG_OK;

@@ -8,10 +8,11 @@
 //
 // Precision.  The reference computes in fp32 and parity is 1e-4 relative, which a single TF32 pass
 // (10-bit mantissa) does not meet.  Every fp32 operand is therefore split x = hi + lo with
-// hi = rn_tf32(x) and lo = rn_tf32(x - hi) (cvt.rna.tf32.f32; x - hi is exact in fp32), and the product is
-// accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32; what is dropped — lo*lo and
-// the rounding of lo — is ~2^-22 relative and unbiased).  B (the weights) is split once per call by k_split_weights; A is split on the fly in
-// shared memory by the CTA's four "splitter" warps, so A crosses HBM once, as plain fp32.
+// hi = rn_tf32(x) and lo = x - hi (exact in fp32), and the product is accumulated in fp32 TMEM as
+// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32; what is dropped — lo*lo and the tensor core's truncation of lo to
+// 11 bits — is ~2^-21 relative).  B (the weights) is split once (k_split_weights, cvt.rna for hi and lo); A is split on
+// the fly in shared memory by the CTA's four "splitter" warps (integer round-to-nearest, 3 instructions per element),
+// so A crosses HBM once, as plain fp32.
 //
 // Persistent CTA = 320 threads, 128 x BLOCK_N output tiles, K in blocks of 32 floats (one 128-byte swizzle row):
 //   warp 0    TMA producer: per stage one box of A (128 x 32) and two of Bt (BLOCK_N x 32: hi, lo),
@@ -20,9 +21,21 @@
 //             tcgen05.commit frees the stage (empty[stage]) and signals tmem_full[buffer] per tile
 //   warps 2-5 splitters: wait full[stage], rewrite the A box in place as hi and write lo to a second
 //             box (element-wise, so swizzle-agnostic), fence.proxy.async, arrive on split_done[stage]
-//   warps 6-9 epilogue: tcgen05.ld their 32 TMEM lanes from the finished accumulator buffer, release it
-//             (tmem_empty[buffer]), transpose through shared memory and apply row scale / column scale+shift /
-//             residual / activation with coalesced global accesses — while the next tile's MMAs run.
+//   warps 6-9 epilogue (6-13 for tiles >= 64 columns): tcgen05.ld their 32 TMEM lanes from the finished accumulator
+//             buffer, release it (tmem_empty[buffer]), apply row scale / column scale+shift / residual / activation /
+//             post-activation shortcut and leave through a swizzled staging tile + TMA store — while the next
+//             tile's MMAs run.
+//
+// Measured lessons built into the epilogue (in-kernel clock64 traces of every role, B200):
+//   * on short-K layers (K <= 128: one to four k-blocks per tile) the epilogue warps, not HBM, set the tile rate.  A
+//     per-column body that re-tested every run-time option (residual? activation? second output? edge?) cost ~4 300
+//     cycles per 32-column chunk; testing each option once per chunk and issuing a side input's loads together brought
+//     conv1 of the finest level from 1 270 to 600 us (4.5 TB/s) and the unary layers to 5.3 TB/s;
+//   * column scale / shift arrive by one coalesced load per lane issued before the accumulator wait + shuffles (with
+//     227 KB of the SM given to shared memory, eight broadcast float4 loads per chunk missed L1);
+//   * tile coordinates use 32-bit division (a 64-bit division by a run-time num_n is a ~100-instruction routine, and
+//     every role ran it per tile);
+//   * a staged tile flushed by coalesced STG.128 instead of the TMA store was 20-40 % slower.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -149,7 +162,6 @@ struct Epilogue {
   const float* addend;     // [M, ld_add]
   int ld2, ld_add;
   int vec_ok;              // every row pointer (C, residual, out2, addend) is 16-byte aligned: float4 accesses allowed
-  int col_vec;             // col_scale / col_shift are 16-byte aligned: float4 broadcast loads allowed
   int tma_store;           // C (and out2) leave through TMA stores from a swizzled shared-memory tile (needs vec_ok)
   const float* post_res;   // [M, ld_post] or null: added AFTER the activation, followed by post_act (a block's shortcut)
   int ld_post;
@@ -657,8 +669,7 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   if (rc) return rc;
   rc = make_map(&mo2, (tma_store && out2) ? out2 : nullptr, m, n, ld2, 32);
   if (rc) return rc;
-  const int col_vec = ((reinterpret_cast<uintptr_t>(col_scale) | reinterpret_cast<uintptr_t>(col_shift)) & 15) == 0;
-  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, col_vec, tma_store,
+  Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, tma_store,
               post_res, ld_post, post_act};
   if (num_hi == 3) {
     if (block_n == 32) return launch_tile_config<32, 3, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
