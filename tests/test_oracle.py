@@ -14,6 +14,10 @@ from conftest import ROOT, rel_err
 LEVEL_KEYS = ("points", "neighbors", "pools", "upsamples", "stack_lengths")
 
 
+def _have_ref():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libkpref.so"))
+
+
 def assert_rows_equal_up_to_ties(got, want, ties, what=""):
     """Index tables must be bit-identical, except inside rows that hold two exactly equal d2: there the
     reference's order is whatever its unstable std::sort leaves (SURVEY.md H2) — a 2-point voxel's
@@ -26,7 +30,27 @@ def assert_rows_equal_up_to_ties(got, want, ties, what=""):
     assert np.array_equal(np.sort(got[ties], 1), np.sort(want[ties], 1)), what
 
 
+def tie_rows_from_reference(oracle, q, s, ql, sl, radius, chunk=65536):
+    """Rows holding two exactly equal d2, from the compiled reference's own (untruncated, ascending-d2) rows: d2 is
+    recomputed in fp32 in nanoflann's order ((dx*dx + dy*dy) + dz*dz, no FMA — numpy rounds every operation) and equal
+    values are adjacent in a sorted row.  Linear in the table size; the port's detector is an O(Nq x Ns) sweep."""
+    q, s = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(s, np.float32)
+    rows = oracle.batch_query(q, s, ql, sl, radius, impl="ref")
+    n_s = s.shape[0]
+    s_pad = np.concatenate([s, np.full((1, 3), np.float32(1e18))], 0)
+    ties = np.zeros(q.shape[0], bool)
+    for a in range(0, q.shape[0], chunk):
+        idx = rows[a:a + chunk]
+        d = q[a:a + chunk, None, :] - s_pad[idx]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        valid = idx < n_s
+        ties[a:a + chunk] = ((d2[:, 1:] == d2[:, :-1]) & valid[:, 1:] & valid[:, :-1]).any(1)
+    return ties
+
+
 def tie_rows(oracle, q, s, ql, sl, radius):
+    if oracle.have_ref() and float(len(q)) * float(len(s)) > 2e9:
+        return tie_rows_from_reference(oracle, q, s, ql, sl, radius)  # full-size clouds: skip the port's quadratic sweep
     return oracle.batch_query(q, s, ql, sl, radius, impl="port", return_ties=True)[1]
 
 
@@ -183,3 +207,23 @@ def test_cuda_table_sizes_match_libstdcxx_header():
     block = block[:block.index("};")]
     cuda_sizes = [int(x) for x in re.findall(r"(\d+)u", block)]
     assert cuda_sizes == sizes[:27]
+
+
+@pytest.mark.skipif(not _have_ref(), reason="needs the compiled reference (oracle/_ref)")
+def test_tie_detector_from_reference_rows_matches_port():
+    """The linear-time tie detector used for full-size clouds marks exactly the rows the port's exhaustive sweep marks."""
+    import kp_oracle
+    from kpreg_b200 import synthetic
+    src, tgt, _ = synthetic.modelnet_pair(seed=5)
+    pts = np.concatenate([src, tgt], 0)
+    lens = np.array([len(src), len(tgt)], np.int32)
+    sub, sub_l = kp_oracle.subsample_batch(pts, lens, sampleDl=0.06, impl="port")
+    for q, s, ql, sl, r in ((pts, pts, lens, lens, 0.0825), (sub, pts, sub_l, lens, 0.0825), (pts, sub, lens, sub_l, 0.165)):
+        want = kp_oracle.batch_query(q, s, ql, sl, r, impl="port", return_ties=True)[1]
+        got = tie_rows_from_reference(kp_oracle, q, s, ql, sl, r)
+        assert np.array_equal(got, want)
+    # a lattice: ties everywhere
+    g = np.stack(np.meshgrid(*[np.arange(6, dtype=np.float32) * 0.05] * 3, indexing="ij"), -1).reshape(-1, 3)
+    gl = np.array([len(g)], np.int32)
+    want = kp_oracle.batch_query(g, g, gl, gl, 0.12, impl="port", return_ties=True)[1]
+    assert want.any() and np.array_equal(tie_rows_from_reference(kp_oracle, g, g, gl, gl, 0.12), want)
