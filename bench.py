@@ -403,6 +403,10 @@ def main():
                 roof["traffic_note"] = (f"bytes per step, all {' + '.join(fam_kernels)} launches (ncu capture at {tr['pairs']} pairs/step "
                                         f"scaled to {args.pairs}; k_gemm_tc also serves the KPConv contraction); achieved / algorithmic "
                                         "figures are per step as well")
+        if roof["traffic"] is None:
+            roof["traffic_note"] = ("no ncu DRAM capture of this build is committed (the round's last launch list was lost to the 64 MiB "
+                                    "copy-back limit); profiles/r1d_dram_traffic.json holds the previous build's: 82 GB per 64-pair step "
+                                    "for all k_gemm_tc launches against 88 GB algorithmic")
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
