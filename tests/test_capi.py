@@ -58,6 +58,25 @@ def test_size_queries_work_without_gpu():
     assert _lib.size_query("kpreg_kpconv_workspace_bytes", 1000, 1000, 15, 32, 32, 0) >= 1000 * 15 * 32 * 4
 
 
+def test_chain_kernel_support_matrix_without_gpu():
+    """kpreg_chain_supported / kpreg_chain_pack_bytes are pure host functions: the res2net widths of the shipped configs
+    (w = floor(C * 14 / 64) for C = 64 .. 1024, 7 chained layers) map to the register-resident kernel up to w = 56."""
+    _ensure_built()
+    lib = _lib.load()
+    want = {14: True, 28: True, 56: True, 112: False, 224: False}
+    for w, ok in want.items():
+        assert bool(lib.kpreg_chain_supported(w, 7)) is ok, w
+    assert not lib.kpreg_chain_supported(27, 7) and not lib.kpreg_chain_supported(28, 0)
+    # packed size = fragments (hi + lo, zero-padded to 8-channel tiles) + shifts, 256-byte granules
+    for w in (14, 28, 56):
+        nt = (w + 7) // 8
+        floats = 7 * (nt * nt * 128 + 8 * nt)
+        assert _lib.size_query("kpreg_chain_pack_bytes", w, 7) == (floats * 4 + 255) // 256 * 256
+    assert _lib.size_query("kpreg_chain_pack_bytes", 56, 7) <= 200 * 1024  # resident in one CTA's shared memory
+    with pytest.raises(RuntimeError):
+        _lib.size_query("kpreg_chain_pack_bytes", 112, 7)
+
+
 def test_product_package_never_touches_the_oracle():
     """The oracle is test infrastructure: no product module may import, load or execute it."""
     offenders = []
