@@ -394,6 +394,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
   }
 }
 
+#ifdef KPREG_EXPERIMENTAL_GATHER_ASYNC
+#include "kpconv_gather_async.cuh"  // cp.async ring variant of the aggregate kernel: not validated on hardware, off by default
+#endif
+
 // ---- c_in == 1 (the encoder's first block: a single input feature per point) ----------------------------
 // With one channel the aggregate is 15 numbers per query and the contraction a [15] x [15, c_out] product, so the whole
 // operator is one kernel: a lane per neighbour evaluates the K influences (fp32 FFMA), a transposing butterfly leaves
@@ -717,6 +721,27 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   } while (0)
     // float4 path: whole rows of x and of the aggregate are 16-byte aligned
     const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
+#ifdef KPREG_EXPERIMENTAL_GATHER_ASYNC
+    static const bool use_async = [] { const char* e = getenv("KPREG_GATHER_ASYNC"); return e && e[0] == '1'; }();
+    if (use_async && vec && c_in > 16 && c_in <= 128) {
+#define KP_GATHER_ASYNC(NT)                                                                                                     \
+  do {                                                                                                                          \
+    const size_t smem = (size_t)kGatherWarps * kRingStages * 16 * NT * sizeof(float4);                                          \
+    if (influence == 1)                                                                                                         \
+      k_kpconv_gather_async<IdxT, NT, 1><<<blocks, kGatherWarps * 32, smem, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, \
+                                                                                      n_nbrs, n_kpts, c_in, extent, influence,   \
+                                                                                      aggregation, agg, inv_num, order);          \
+    else                                                                                                                        \
+      k_kpconv_gather_async<IdxT, NT, -1><<<blocks, kGatherWarps * 32, smem, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, \
+                                                                                       n_nbrs, n_kpts, c_in, extent, influence,  \
+                                                                                       aggregation, agg, inv_num, order);         \
+  } while (0)
+      if (c_in <= 32) KP_GATHER_ASYNC(4); else if (c_in <= 64) KP_GATHER_ASYNC(8); else KP_GATHER_ASYNC(16);
+#undef KP_GATHER_ASYNC
+      KP_LAUNCH_CHECK();
+      return KPREG_OK;
+    }
+#endif
     if (c_in <= 8) KP_GATHER_MMA(1, false);
     else if (c_in <= 16) KP_GATHER_MMA(2, false);
     else if (c_in <= 32) { if (vec) KP_GATHER_MMA(4, true); else KP_GATHER_MMA(4, false); }
