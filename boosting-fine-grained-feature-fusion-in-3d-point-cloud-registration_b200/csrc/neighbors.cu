@@ -13,12 +13,30 @@
 //   computed in fp64 so that a neighbour within r can never be more than one cell away;
 //   supports are radix-sorted by key into a float4 array (xyz + local index); every occupied cell
 //   gets a [start,end) range in an open-addressing hash table (64-bit keys, linear probing).
-// Query (one warp per query point):
-//   lanes 0..26 look up the 27 surrounding cells; the warp then walks the concatenated ranges 32
+// Query, hot path (k_grid_query_tq, row width <= 56): ONE THREAD PER QUERY, 32 consecutive queries of the cell-sorted
+// processing order per warp.
+//   * The warp's queries fall into a handful of x-adjacent cells.  Lanes whose cells lie within a small window of the
+//     first pending lane's cell form a group; the group's candidate set is the bounding box of its cells grown by one
+//     cell.  Because cx is the lowest key field, the occupied cells of one (cloud, cz, cy) row of the box are ONE
+//     contiguous span of the sorted support array: 9 .. 25 spans per group instead of 27 hash look-ups + a per-candidate
+//     binary search per query.  (Cells are probed once per group, lanes in parallel; span ends land in shared memory.)
+//   * Every lane then tests every candidate of the box against its own query: the candidate's float4 is one
+//     warp-uniform load (a broadcast, served by L1 — the spans are shared by the CTA's warps and by consecutive
+//     iterations), ~12 instructions per candidate for 32 queries at once.  A warp per query spent ~50 instructions per
+//     32 candidates on ONE query: the old kernel was instruction-issue bound at 2 % of the HBM roofline.
+//   * Hits are appended to the lane's own list in shared memory ([lane][CAP+1] 64-bit (d2 bits << 32 | index) keys —
+//     the odd pitch makes both the per-lane and the per-row access patterns conflict-free), sorted per lane by
+//     insertion (32 lists in lock step), and the rows are written out cooperatively: one row = one contiguous,
+//     coalesced store of the whole warp.
+//   * A lane with more than CAP (= 64) hits is finished by the warp-cooperative exact routine below (exact_query_warp).
+// Query, general path (k_grid_query, any width, also the count-only pass): one warp per query through
+// exact_query_warp: lanes 0..26 look up the 27 surrounding cells; the warp then walks the concatenated ranges 32
 //   candidates at a time (coalesced 16-byte loads), compacts the hits with a ballot into shared
 //   memory as 64-bit (d2 bits << 32 | index) keys, ranks them by counting and writes each index at its rank
 //   (a row is one contiguous 4*width-byte span, so the scattered 4-byte stores of a warp fall into 1-2 lines).
 #include <cub/cub.cuh>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -205,6 +223,109 @@ __device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float s
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// One query, the whole warp: the exact neighbour row of (qx,qy,qz) for ANY hit count.  All arguments are warp-uniform.
+// `hits` is a per-warp shared-memory buffer of hit_cap keys, s_cell_start / s_cell_prefix hold 32 ints each.
+// Writes the row (indices + padding) and returns the number of supports within the radius.
+template <typename OutT>
+__device__ __forceinline__ int exact_query_warp(const GridHeader& h, const float4* __restrict__ sorted,
+                                                const uint64_t* __restrict__ tab_key, const int2* __restrict__ tab_val, uint32_t cap,
+                                                float qx, float qy, float qz, int cloud, int cx, int cy, int cz, float r2, int width,
+                                                OutT* __restrict__ row, int64_t cloud_base, int64_t n_supports,
+                                                unsigned long long* __restrict__ hits, int hit_cap, int* __restrict__ s_cell_start,
+                                                int* __restrict__ s_cell_prefix) {
+  const int lane = threadIdx.x & 31;
+  // lanes 0..26: one surrounding cell each
+  int start = 0, len = 0;
+  if (lane < 27) {
+    const int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
+    if (nx >= 0 && ny >= 0 && nz >= 0 && nx < h.dims[0] && ny < h.dims[1] && nz < h.dims[2]) {
+      const int2 rng = table_find(tab_key, tab_val, cap, make_key(cloud, nx, ny, nz));
+      start = rng.x;
+      len = rng.y - rng.x;
+    }
+  }
+  const int incl = warp_scan_inclusive(len);
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  __syncwarp();
+  s_cell_start[lane] = start;
+  s_cell_prefix[lane] = incl - len;  // exclusive prefix
+  __syncwarp();
+
+  int count = 0;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    bool hit = false;
+    unsigned long long packed = 0ull;
+    if (t < total) {
+      // last cell whose exclusive prefix is <= t (prefixes are non-decreasing; empty cells repeat)
+      int lo = 0, hi = 27;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_cell_prefix[mid] <= t) lo = mid; else hi = mid;
+      }
+      const float4 sp = sorted[s_cell_start[lo] + (t - s_cell_prefix[lo])];
+      const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+      hit = d2 < r2;
+      packed = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = count + __popc(mask & ((1u << lane) - 1u));
+      if (pos < hit_cap) hits[pos] = packed;
+    }
+    count += __popc(mask);
+  }
+  __syncwarp();
+  if (count <= hit_cap) {
+    // rank by counting: keys are distinct (distinct indices), so rank = number of smaller keys.  (A warp-wide
+    // bitonic sort of the buffer was measured slower: its ~21-28 dependent shared-memory stages are latency-bound,
+    // while these comparisons are independent and pipeline.)
+    for (int e = lane; e < count; e += 32) {
+      const unsigned long long mine = hits[e];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < count; ++j) rank += (hits[j] < mine) ? 1 : 0;
+      if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
+    }
+  } else {
+    // more hits than the shared buffer holds: recount from the candidate ranges (rare, exact, slow)
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      unsigned long long mine = 0ull;
+      if (t < total) {
+        int lo = 0, hi = 27;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_cell_prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        const float4 sp = sorted[s_cell_start[lo] + (t - s_cell_prefix[lo])];
+        const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+        hit = d2 < r2;
+        mine = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+      }
+      if (hit) {
+        int rank = 0;
+        for (int cidx = 0; cidx < 27; ++cidx) {
+          const int cs = s_cell_start[cidx];
+          const int ce = cs + ((cidx < 26 ? s_cell_prefix[cidx + 1] : total) - s_cell_prefix[cidx]);
+          for (int j = cs; j < ce; ++j) {
+            const float4 o = sorted[j];
+            const float od2 = dist2_ref(qx, qy, qz, o.x, o.y, o.z);
+            const unsigned long long ok = ((unsigned long long)__float_as_uint(od2) << 32) | (unsigned int)__float_as_int(o.w);
+            rank += (od2 < r2 && ok < mine) ? 1 : 0;
+          }
+        }
+        if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
+      }
+    }
+  }
+  for (int e = count + lane; e < width; e += 32) row[e] = (OutT)n_supports;
+  __syncwarp();
+  return count;
+}
+
+// General path: one warp per query (any row width, also the count-only pass with width 0).
 template <typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
     const GridHeader* __restrict__ hdr, const int64_t* __restrict__ s_off, int n_clouds, int64_t n_supports,
@@ -220,7 +341,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
   __syncthreads();
   const GridHeader h = *hdr;
   int my_max = 0;
-  unsigned long long* hits = s_hits[warp];
 
   // each CTA owns a contiguous slice of the (cell-sorted) processing order: its queries share cells -> L1 hits
   const int64_t per_cta = (n_queries + gridDim.x - 1) / gridDim.x;
@@ -229,102 +349,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
     const int64_t qi = order ? (int64_t)order[it] : it;  // processing order only, never the result
     const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
     const int cloud = cloud_of(q_off, n_clouds, qi);
-    const int64_t cloud_base = s_off[cloud];
     int cx, cy, cz;
     cell_coords(h, qx, qy, qz, cx, cy, cz);
     cx = min(max(cx, -2), kCellMax + 2);
     cy = min(max(cy, -2), kCellMax + 2);
     cz = min(max(cz, -2), kCellMax + 2);
-    // lanes 0..26: one surrounding cell each
-    int start = 0, len = 0;
-    if (lane < 27) {
-      const int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
-      if (nx >= 0 && ny >= 0 && nz >= 0 && nx < h.dims[0] && ny < h.dims[1] && nz < h.dims[2]) {
-        const int2 rng = table_find(tab_key, tab_val, cap, make_key(cloud, nx, ny, nz));
-        start = rng.x;
-        len = rng.y - rng.x;
-      }
-    }
-    const int incl = warp_scan_inclusive(len);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    s_cell_start[warp][lane] = start;
-    s_cell_prefix[warp][lane] = incl - len;  // exclusive prefix
-    __syncwarp();
-
-    int count = 0;
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      bool hit = false;
-      unsigned long long packed = 0ull;
-      if (t < total) {
-        // last cell whose exclusive prefix is <= t (prefixes are non-decreasing; empty cells repeat)
-        int lo = 0, hi = 27;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (s_cell_prefix[warp][mid] <= t) lo = mid; else hi = mid;
-        }
-        const float4 sp = sorted[s_cell_start[warp][lo] + (t - s_cell_prefix[warp][lo])];
-        const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
-        hit = d2 < r2;
-        packed = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
-      }
-      const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = count + __popc(mask & ((1u << lane) - 1u));
-        if (pos < kHitCap) hits[pos] = packed;
-      }
-      count += __popc(mask);
-    }
-    __syncwarp();
-    OutT* row = out + qi * (int64_t)width;
-    if (count <= kHitCap) {
-      // rank by counting: keys are distinct (distinct indices), so rank = number of smaller keys.  (A warp-wide
-      // bitonic sort of the buffer was measured slower: its ~21-28 dependent shared-memory stages are latency-bound,
-      // while these comparisons are independent and pipeline.)
-      for (int e = lane; e < count; e += 32) {
-        const unsigned long long mine = hits[e];
-        int rank = 0;
-#pragma unroll 4
-        for (int j = 0; j < count; ++j) rank += (hits[j] < mine) ? 1 : 0;
-        if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
-      }
-    } else {
-      // more hits than the shared buffer holds: recount from the candidate ranges (rare, exact, slow)
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        bool hit = false;
-        unsigned long long mine = 0ull;
-        if (t < total) {
-          int lo = 0, hi = 27;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_cell_prefix[warp][mid] <= t) lo = mid; else hi = mid;
-          }
-          const float4 sp = sorted[s_cell_start[warp][lo] + (t - s_cell_prefix[warp][lo])];
-          const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
-          hit = d2 < r2;
-          mine = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
-        }
-        if (hit) {
-          int rank = 0;
-          for (int cidx = 0; cidx < 27; ++cidx) {
-            const int cs = s_cell_start[warp][cidx];
-            const int ce = cs + ((cidx < 26 ? s_cell_prefix[warp][cidx + 1] : total) - s_cell_prefix[warp][cidx]);
-            for (int j = cs; j < ce; ++j) {
-              const float4 o = sorted[j];
-              const float od2 = dist2_ref(qx, qy, qz, o.x, o.y, o.z);
-              const unsigned long long ok = ((unsigned long long)__float_as_uint(od2) << 32) | (unsigned int)__float_as_int(o.w);
-              rank += (od2 < r2 && ok < mine) ? 1 : 0;
-            }
-          }
-          if (rank < width) row[rank] = (OutT)((int64_t)(unsigned int)(mine & 0xffffffffull) + cloud_base);
-        }
-      }
-    }
-    for (int e = count + lane; e < width; e += 32) row[e] = (OutT)n_supports;
+    const int count = exact_query_warp<OutT>(h, sorted, tab_key, tab_val, cap, qx, qy, qz, cloud, cx, cy, cz, r2, width,
+                                             out + qi * (int64_t)width, s_off[cloud], n_supports, s_hits[warp], kHitCap,
+                                             s_cell_start[warp], s_cell_prefix[warp]);
     if (out_counts != nullptr && lane == 0) out_counts[qi] = count;
     my_max = max(my_max, count);
-    __syncwarp();
   }
   if (lane == 0 && my_max > 0) atomicMax(&s_block_max, my_max);
   __syncthreads();
@@ -332,6 +366,160 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
     if (s_block_max > 0) atomicMax(out_stats, s_block_max);
     if (h.status != 0) atomicMax(out_stats + 1, h.status);
     // the 27-cell sweep is only exhaustive while the query radius does not exceed the cell edge
+    if ((double)radius * (1.0 + 5e-7) * h.inv_cell > 1.0) atomicMax(out_stats + 1, (int32_t)KPREG_E_RANGE);
+  }
+}
+
+// ---- hot path: one thread per query ------------------------------------------------------------------------------
+constexpr int kTqWarps = 4;       // warps (= 32-query blocks in flight) per CTA
+constexpr int kTqCap = 64;        // hits a lane buffers; more -> exact_query_warp
+constexpr int kTqPitch = kTqCap + 1;  // odd pitch (in 8-byte keys): lane-own and row-cooperative accesses are both conflict-free
+constexpr int kTqMaxWidth = 56;   // row widths served by this kernel
+constexpr int kTqSpan = 6;        // a group's cells lie within +-kTqSpan (x) / +-1 (y, z) of its first lane's cell
+constexpr int kTqMaxRows = 25;    // (3 + 2)^2 (cy, cz) rows of a group's box at most
+constexpr size_t kTqSmemBytes = (size_t)kTqWarps * (32 * kTqPitch * 8 + 64 * 4);
+
+template <typename OutT>
+__global__ void __launch_bounds__(kTqWarps * 32) k_grid_query_tq(
+    const GridHeader* __restrict__ hdr, const int64_t* __restrict__ s_off, int n_clouds, int64_t n_supports,
+    const float4* __restrict__ sorted, const uint64_t* __restrict__ tab_key, const int2* __restrict__ tab_val, uint32_t cap,
+    const float* __restrict__ queries, const int64_t* __restrict__ q_off, int64_t n_queries, float radius, float r2, int width,
+    OutT* __restrict__ out, int32_t* __restrict__ out_counts, int32_t* __restrict__ out_stats, const int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char tq_smem[];
+  __shared__ int s_block_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* const warp_hits = reinterpret_cast<unsigned long long*>(tq_smem) + (size_t)warp * (32 * kTqPitch);
+  unsigned long long* const my_hits = warp_hits + lane * kTqPitch;
+  int* const s_row_start = reinterpret_cast<int*>(tq_smem + (size_t)kTqWarps * 32 * kTqPitch * 8) + warp * 64;
+  int* const s_row_end = s_row_start + 32;
+  if (threadIdx.x == 0) s_block_max = 0;
+  __syncthreads();
+  const GridHeader h = *hdr;
+  int my_max = 0;
+
+  // each CTA owns a contiguous slice of the (cell-sorted) processing order; its warps take alternate 32-query blocks
+  const int64_t n_blocks = (n_queries + 31) >> 5;
+  const int64_t per_cta = (n_blocks + gridDim.x - 1) / gridDim.x;
+  const int64_t blk_end = min(n_blocks, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t blk = (int64_t)blockIdx.x * per_cta + warp; blk < blk_end; blk += kTqWarps) {
+    const int64_t it = (blk << 5) + lane;
+    const bool valid = it < n_queries;
+    int64_t qi = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int cloud = -1, cx = 0, cy = 0, cz = 0;
+    int64_t cloud_base = 0;
+    if (valid) {
+      qi = order ? (int64_t)order[it] : it;  // processing order only, never the result
+      qx = queries[3 * qi]; qy = queries[3 * qi + 1]; qz = queries[3 * qi + 2];
+      cloud = cloud_of(q_off, n_clouds, qi);
+      cloud_base = s_off[cloud];
+      cell_coords(h, qx, qy, qz, cx, cy, cz);
+      cx = min(max(cx, -2), kCellMax + 2);
+      cy = min(max(cy, -2), kCellMax + 2);
+      cz = min(max(cz, -2), kCellMax + 2);
+    }
+    int count = 0;
+    unsigned int pending = __ballot_sync(0xffffffffu, valid);
+    while (pending) {
+      // group = the pending lanes whose cell lies in a small window around the first pending lane's cell
+      const int head = __ffs(pending) - 1;
+      const int hcloud = __shfl_sync(0xffffffffu, cloud, head);
+      const int hcx = __shfl_sync(0xffffffffu, cx, head), hcy = __shfl_sync(0xffffffffu, cy, head),
+                hcz = __shfl_sync(0xffffffffu, cz, head);
+      const bool member = ((pending >> lane) & 1u) && cloud == hcloud && abs(cx - hcx) <= kTqSpan && abs(cy - hcy) <= 1 &&
+                          abs(cz - hcz) <= 1;
+      pending &= ~__ballot_sync(0xffffffffu, member);
+      // bounding box of the group's cells, grown by one cell, clipped to the grid
+      const int bx0 = max(__reduce_min_sync(0xffffffffu, member ? cx : 0x7fffffff) - 1, 0);
+      const int by0 = max(__reduce_min_sync(0xffffffffu, member ? cy : 0x7fffffff) - 1, 0);
+      const int bz0 = max(__reduce_min_sync(0xffffffffu, member ? cz : 0x7fffffff) - 1, 0);
+      const int bx1 = min(__reduce_max_sync(0xffffffffu, member ? cx : -0x7fffffff) + 1, h.dims[0] - 1);
+      const int by1 = min(__reduce_max_sync(0xffffffffu, member ? cy : -0x7fffffff) + 1, h.dims[1] - 1);
+      const int bz1 = min(__reduce_max_sync(0xffffffffu, member ? cz : -0x7fffffff) + 1, h.dims[2] - 1);
+      if (bx0 > bx1 || by0 > by1 || bz0 > bz1) continue;  // the whole group lies outside the grid: no neighbours
+      const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1, n_rows = nby * (bz1 - bz0 + 1);
+      // every (cz, cy) row of the box: the span of the sorted array its occupied cells cover
+      __syncwarp();
+      s_row_start[lane] = 0x7fffffff;
+      s_row_end[lane] = 0;
+      __syncwarp();
+      const int n_cells = n_rows * nbx;
+      for (int c = lane; c < n_cells; c += 32) {
+        const int r = c / nbx, xi = c - r * nbx;
+        const int rz = r / nby, ry = r - rz * nby;
+        const int2 rng = table_find(tab_key, tab_val, cap, make_key(hcloud, bx0 + xi, by0 + ry, bz0 + rz));
+        if (rng.y > rng.x) {
+          atomicMin(&s_row_start[r], rng.x);
+          atomicMax(&s_row_end[r], rng.y);
+        }
+      }
+      __syncwarp();
+      // every lane tests every candidate of the box against its own query
+      auto test = [&](const float4& sp) {
+        const float d2 = dist2_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+        if (member && d2 < r2) {
+          if (count < kTqCap) my_hits[count] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+          ++count;
+        }
+      };
+      for (int r = 0; r < n_rows; ++r) {
+        const int rs = s_row_start[r], re = s_row_end[r];  // warp-uniform
+        if (rs >= re) continue;
+        int j = rs;
+        for (; j + 4 <= re; j += 4) {
+          const float4 c0 = __ldg(sorted + j), c1 = __ldg(sorted + j + 1), c2 = __ldg(sorted + j + 2), c3 = __ldg(sorted + j + 3);
+          test(c0); test(c1); test(c2); test(c3);
+        }
+        for (; j < re; ++j) test(__ldg(sorted + j));
+      }
+    }
+    // per-lane insertion sort of the buffered keys (ascending (d2, index)); 32 lists in lock step
+    const bool overflow = count > kTqCap;
+    const int n_sort = overflow ? 0 : count;
+    for (int i = 1; i < n_sort; ++i) {
+      const unsigned long long key = my_hits[i];
+      int j = i;
+      while (j > 0) {
+        const unsigned long long prev = my_hits[j - 1];
+        if (prev <= key) break;
+        my_hits[j] = prev;
+        --j;
+      }
+      my_hits[j] = key;
+    }
+    __syncwarp();
+    // rows leave cooperatively: row r = one contiguous span written by the whole warp
+    const unsigned int vmask = __ballot_sync(0xffffffffu, valid && !overflow);
+    for (int r = 0; r < 32; ++r) {
+      if (!((vmask >> r) & 1u)) continue;
+      const int64_t rq = __shfl_sync(0xffffffffu, qi, r), rbase = __shfl_sync(0xffffffffu, cloud_base, r);
+      const int rn = __shfl_sync(0xffffffffu, n_sort, r);
+      OutT* __restrict__ row = out + rq * (int64_t)width;
+      const unsigned long long* __restrict__ rh = warp_hits + r * kTqPitch;
+      for (int e = lane; e < width; e += 32)
+        row[e] = e < rn ? (OutT)((int64_t)(unsigned int)(rh[e] & 0xffffffffull) + rbase) : (OutT)n_supports;
+    }
+    __syncwarp();
+    // lanes that buffered too many hits: the exact warp-cooperative routine, one query at a time (the lists are free now)
+    unsigned int ov = __ballot_sync(0xffffffffu, valid && overflow);
+    while (ov) {
+      const int l = __ffs(ov) - 1;
+      ov &= ov - 1;
+      const int64_t oq = __shfl_sync(0xffffffffu, qi, l), obase = __shfl_sync(0xffffffffu, cloud_base, l);
+      exact_query_warp<OutT>(h, sorted, tab_key, tab_val, cap, __shfl_sync(0xffffffffu, qx, l), __shfl_sync(0xffffffffu, qy, l),
+                             __shfl_sync(0xffffffffu, qz, l), __shfl_sync(0xffffffffu, cloud, l), __shfl_sync(0xffffffffu, cx, l),
+                             __shfl_sync(0xffffffffu, cy, l), __shfl_sync(0xffffffffu, cz, l), r2, width, out + oq * (int64_t)width,
+                             obase, n_supports, warp_hits, 32 * kTqPitch, s_row_start, s_row_end);
+    }
+    if (out_counts != nullptr && valid) out_counts[qi] = count;
+    my_max = max(my_max, __reduce_max_sync(0xffffffffu, count));
+  }
+  if (lane == 0 && my_max > 0) atomicMax(&s_block_max, my_max);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_block_max > 0) atomicMax(out_stats, s_block_max);
+    if (h.status != 0) atomicMax(out_stats + 1, h.status);
+    // the one-cell margin of a group's box is only exhaustive while the query radius does not exceed the cell edge
     if ((double)radius * (1.0 + 5e-7) * h.inv_cell > 1.0) atomicMax(out_stats + 1, (int32_t)KPREG_E_RANGE);
   }
 }
@@ -410,10 +598,30 @@ extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const
   int rc = launch_cloud_offsets(q_lens, n_clouds, q_off, stream);
   if (rc) return rc;
   const float r2 = radius * radius;  // neighbors.cpp:226, fp32
+  ProfScope prof(KPREG_FAM_GRID_QUERY, stream);
+  static const bool force_general = [] { const char* e = getenv("KPREG_QUERY_GENERAL"); return e && e[0] == '1'; }();  // A/B measurements
+  if (width >= 1 && width <= kTqMaxWidth && !force_general) {
+    // hot path: one thread per query, 32-query blocks of the processing order per warp
+    int blocks = ceil_div(ceil_div(n_queries, 32), kTqWarps);
+    const int max_blocks = kNumSMs * 24;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (idx64) {
+      KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+      k_grid_query_tq<int64_t><<<blocks, kTqWarps * 32, kTqSmemBytes, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
+                                                                                 w.tab_cap, queries, q_off, n_queries, radius, r2, width,
+                                                                                 static_cast<int64_t*>(out_idx), out_counts, out_stats, order);
+    } else {
+      KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+      k_grid_query_tq<int32_t><<<blocks, kTqWarps * 32, kTqSmemBytes, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
+                                                                                 w.tab_cap, queries, q_off, n_queries, radius, r2, width,
+                                                                                 static_cast<int32_t*>(out_idx), out_counts, out_stats, order);
+    }
+    KP_LAUNCH_CHECK();
+    return KPREG_OK;
+  }
   int blocks = ceil_div(n_queries, kWarpsPerBlock);
   const int max_blocks = kNumSMs * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  ProfScope prof(KPREG_FAM_GRID_QUERY, stream);
   if (idx64) {
     k_grid_query<int64_t><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab_key, w.tab_val,
                                                                      w.tab_cap, queries, q_off, n_queries, radius, r2, width,

@@ -2,7 +2,7 @@
 
 CPU restatement of the reference's KPConv hot path.  Only ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this module; the
-product package never does (tests/test_no_oracle_in_product.py enforces it).
+product package never does (tests/test_capi.py::test_product_package_never_touches_the_oracle enforces it).
 
 Two native back ends sit behind the same functions:
 
@@ -375,6 +375,22 @@ def encoder_forward(sd: Dict[str, torch.Tensor], cfg, x, batch, training: bool =
 # --------------------------------------------------------------------------------------------
 # Weighted Kabsch
 # --------------------------------------------------------------------------------------------
+
+def compute_overlaps(src_overlap, tgt_overlap, pools, level_sizes) -> List[np.ndarray]:
+    """Per-level ground-truth overlap ratios (reference models/backbone_kpconv/finegrained_kpconv.py:545-571):
+    level 0 = the per-point masks as float; level p = mean of level p-1 over the valid entries of pools[p-1]
+    (index < row count of level p-1), clamped to [0, 1].  A row without a valid entry is 0/0 = nan, as in the reference."""
+    level = np.concatenate([np.asarray(src_overlap), np.asarray(tgt_overlap)]).astype(np.float32)
+    out = [level]
+    for p in range(1, len(level_sizes)):
+        idx = np.asarray(pools[p - 1]).astype(np.int64)
+        valid = idx < int(level_sizes[p - 1])
+        gathered = level[np.where(valid, idx, 0)] * valid
+        with np.errstate(invalid="ignore", divide="ignore"):
+            level = np.clip(gathered.sum(1, dtype=np.float32) / valid.sum(1).astype(np.float32), 0.0, 1.0).astype(np.float32)
+        out.append(level)
+    return out
+
 
 def compute_rigid_transform(a, b, weights=None) -> torch.Tensor:
     """compute_rigid_transform (utils/se3_torch.py:131-173), torch CPU fp32, LAPACK SVD."""

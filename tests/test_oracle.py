@@ -227,3 +227,54 @@ def test_tie_detector_from_reference_rows_matches_port():
     gl = np.array([len(g)], np.int32)
     want = kp_oracle.batch_query(g, g, gl, gl, 0.12, impl="port", return_ties=True)[1]
     assert want.any() and np.array_equal(tie_rows_from_reference(kp_oracle, g, g, gl, gl, 0.12), want)
+
+
+def r2_state_dict(g, prefix, enc):
+    """Seeded weights (tests/seeded_weights.py) + the fixture's kernel points for an encoder of the fixture's shape."""
+    import torch as _t
+    from seeded_weights import seeded_state_dict
+    sd = seeded_state_dict(enc.state_dict())
+    for k in sd:
+        if k.endswith("kernel_points"):
+            sd[k] = _t.from_numpy(g[f"{prefix}_kp::{k}"])
+    return sd
+
+
+def r2_case(g, prefix):
+    """(cfg, d_bottle, [src, tgt]) of an encoder_r2.npz case."""
+    if prefix == "tdm":
+        cfg = kpconv_config("3dmatch")
+        src, tgt, _ = synthetic.threedmatch_pair(seed=2, n_raw=9000)
+        return cfg, cfg.d_embed, [src, tgt]
+    cfg = kpconv_config("modelnet", first_feats_dim=128)
+    src, tgt, _ = synthetic.modelnet_pair(seed=1)
+    return cfg, 256, [src, tgt]
+
+
+@pytest.mark.parametrize("prefix", ["tdm", "mn128"])
+def test_oracle_encoder_matches_reference_r2_fixture(oracle, golden_encoder_r2, prefix):
+    """The port's encoder against the REFERENCE KPFEncoder on the shipped 3DMatch configuration (res2net widths
+    28 / 56 / 112 / 224) and on the ModelNet architecture at width 28 — the widths this repo's fused path serves."""
+    from kpreg_b200.kpconv import KPFEncoder
+    g = golden_encoder_r2
+    cfg, d_bottle, clouds = r2_case(g, prefix)
+    np.random.seed(0)
+    sd = r2_state_dict(g, prefix, KPFEncoder(cfg, d_bottle))
+    meta = oracle.preprocess(clouds, cfg, impl="ref" if oracle.have_ref() else "port")
+    x0 = np.ones((meta["points"][0].shape[0], 1), np.float32)
+    y, skips = oracle.encoder_forward(sd, cfg, x0, meta)
+    assert y.shape == g[f"{prefix}_enc_out"].shape
+    err = rel_err(y.numpy(), g[f"{prefix}_enc_out"])
+    stride = int(g[f"{prefix}_row_stride"])
+    errs = [rel_err(s.numpy()[::stride], g[f"{prefix}_skip_{i}_rows"]) for i, s in enumerate(skips)]
+    print(f"oracle port vs reference KPFEncoder ({prefix}): out {err:.2e}, skips {['%.1e' % e for e in errs]}")
+    assert err < 1e-4 and max(errs) < 1e-4
+
+
+def test_oracle_compute_overlaps_matches_reference_fixture(oracle, golden_3dmatch, golden_overlaps_r2):
+    g, ov = golden_3dmatch, golden_overlaps_r2
+    want = golden_pyramid_3dmatch(g)
+    pyr = oracle.compute_overlaps(ov["src_overlap"], ov["tgt_overlap"], want["pools"], [p.shape[0] for p in want["points"]])
+    assert len(pyr) == 4
+    for p in range(4):
+        assert float(np.abs(pyr[p] - ov[f"pyr_{p}"]).max()) < 1e-6, p  # sums of <= 40 fp32 terms: order-of-summation slack only
