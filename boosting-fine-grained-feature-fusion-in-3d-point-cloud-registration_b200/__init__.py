@@ -11,5 +11,14 @@ tables, KPConv and weighted Kabsch as hand-written CUDA kernels behind a C ABI
 from . import _lib  # noqa: F401  (ctypes binding; the library is loaded on first use)
 from .config import AttrDict, kpconv_config  # noqa: F401
 
-__all__ = ["AttrDict", "kpconv_config"]
+
+
+def invalidate_caches() -> None:
+    """Drop the inference caches of derived weights (see ops.invalidate_caches): call after writing parameters or
+    BatchNorm statistics through ``.data`` — such writes do not bump the version counters the caches are checked by."""
+    from . import ops
+    ops.invalidate_caches()
+
+
+__all__ = ["AttrDict", "kpconv_config", "invalidate_caches"]
 __version__ = "0.1.0"

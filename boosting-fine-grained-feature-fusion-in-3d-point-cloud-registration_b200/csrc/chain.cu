@@ -212,11 +212,12 @@ template <int NT>
 int launch_chain(const float* t, int ld_t, const float* pack, int w, int n_layers, int64_t m_rows, float* z, int ld_z,
                  const float* x_copy, int ld_x, int c_x, cudaStream_t stream) {
   const size_t smem = chain_smem_bytes(w, n_layers);
-  static size_t configured = 0;
-  if (smem > configured) {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_chain<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static PerDeviceOnce once;  // per device: the largest footprint kpreg_chain_supported admits
+  const int rc_cfg = once.run([]() -> int {
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_chain<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return KPREG_OK;
+  });
+  if (rc_cfg) return rc_cfg;
   const int per_sm = (NT <= 4 && 2 * smem <= 200 * 1024) ? 2 : 1;
   int blocks = ceil_div(m_rows, kChainRows);
   if (blocks > per_sm * kNumSMs) blocks = per_sm * kNumSMs;

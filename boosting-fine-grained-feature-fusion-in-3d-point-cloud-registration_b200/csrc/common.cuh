@@ -49,6 +49,23 @@ static inline int bits_for(uint64_t n) {  // bits needed to represent values < n
   return b;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: call `configure` once per device ordinal and
+// kernel (thread-safe; one atomic load on the hot path).  A process that drives several GPUs therefore configures each.
+struct PerDeviceOnce {
+  unsigned long long done[2] = {0ull, 0ull};  // one bit per device ordinal (0..127)
+  template <typename F>
+  int run(F&& configure) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return configure();
+    unsigned long long* word = &done[dev >> 6];
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(word, __ATOMIC_ACQUIRE) & bit) return KPREG_OK;
+    const int rc = configure();
+    if (rc == KPREG_OK) __atomic_fetch_or(word, bit, __ATOMIC_RELEASE);
+    return rc;
+  }
+};
+
 // Bump allocator over a caller-provided workspace (256-byte aligned carve-outs).
 struct Carver {
   char* base;

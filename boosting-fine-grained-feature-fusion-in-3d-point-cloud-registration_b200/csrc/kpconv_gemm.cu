@@ -597,11 +597,12 @@ template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
 int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
                        const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;  // (the attribute is per device: a second GPU in the same process needs its own call)
+  const int rc_cfg = once.run([]() -> int {
     KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
-    configured = true;
-  }
+    return KPREG_OK;
+  });
+  if (rc_cfg) return rc_cfg;
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);

@@ -708,12 +708,22 @@ extern "C" int kpreg_grid_query(const void* grid, int64_t n, int n_clouds, const
     // hot path: one thread per query, 32-query blocks of the processing order per warp
     const int blocks = ceil_div(ceil_div(n_queries, 32), kTqWarps);  // n_queries < 2^31 rows (checked above): fits a grid
     if (idx64) {
-      KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+      static PerDeviceOnce once;
+      const int rc_cfg = once.run([]() -> int {
+        KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+        return KPREG_OK;
+      });
+      if (rc_cfg) return rc_cfg;
       k_grid_query_tq<int64_t><<<blocks, kTqWarps * 32, kTqSmemBytes, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab,
                                                                                  w.tab_cap, queries, q_off, n_queries, radius, r2, width,
                                                                                  static_cast<int64_t*>(out_idx), out_counts, out_stats, order);
     } else {
-      KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+      static PerDeviceOnce once;
+      const int rc_cfg = once.run([]() -> int {
+        KP_CUDA_TRY(cudaFuncSetAttribute(k_grid_query_tq<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTqSmemBytes));
+        return KPREG_OK;
+      });
+      if (rc_cfg) return rc_cfg;
       k_grid_query_tq<int32_t><<<blocks, kTqWarps * 32, kTqSmemBytes, stream>>>(w.hdr, w.off, n_clouds, n, w.sorted, w.tab,
                                                                                  w.tab_cap, queries, q_off, n_queries, radius, r2, width,
                                                                                  static_cast<int32_t*>(out_idx), out_counts, out_stats, order);

@@ -103,7 +103,7 @@ class _KPConvFn(torch.autograd.Function):
         return None, None, None, d_x, d_w, None, None, None, None, None, None
 
 
-class KPConv(nn.Module):
+class KPConv(ops.CacheInvalidatingModule):
 
     def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
                  fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
@@ -205,7 +205,7 @@ class BatchNormBlock(nn.Module):
             self.in_dim, self.bn_momentum, str(not self.use_bn))
 
 
-class UnaryBlock(nn.Module):
+class UnaryBlock(ops.CacheInvalidatingModule):
 
     def __init__(self, in_dim, out_dim, use_bn, bn_momentum, no_relu=False):
         super().__init__()

@@ -7,12 +7,30 @@ neighbour row widths) are returned as small device tensors; the callers in ``cpp
 """
 from __future__ import annotations
 
-import weakref
+import contextlib
+import functools
+from torch.utils.weak import WeakIdKeyDictionary
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first tensor argument current.  The C entry points launch on the current
+    device, so tensors living on another GPU of the same process (one process driving several GPUs) need the switch;
+    when the devices already agree — one process per GPU, the normal case — this is one integer comparison."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
 
 INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
 AGGREGATION = {"sum": 0, "closest": 1}
@@ -37,10 +55,21 @@ def _idx(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     return t.to(torch.int64).contiguous(), 1
 
 
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _device_of(t: torch.Tensor):
+    """Context manager making ``t``'s CUDA device current (a no-op object when it already is)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+        return torch.cuda.device(t.device)
+    return _NULL_CTX
+
+
 # ------------------------------------------------------------------------------------------------
 # subsampling
 # ------------------------------------------------------------------------------------------------
 
+@_on_tensor_device
 def subsample(points: torch.Tensor, lens: torch.Tensor, sample_dl: float, max_p: int = 0):
     """Voxel-grid barycentres of a stacked batch (kpreg_subsample_batch).
 
@@ -72,6 +101,10 @@ class CellGrid:
     radius <= cell for any query set of the same batch (kpreg_grid_query)."""
 
     def __init__(self, supports: torch.Tensor, s_lens: torch.Tensor, cell: float, want_order: bool = True):
+        with _device_of(supports):
+            self._build(supports, s_lens, cell, want_order)
+
+    def _build(self, supports, s_lens, cell, want_order):
         lib = _lib.load()
         self.supports = _f32c(supports, "supports")
         self.s_lens = _i32c(s_lens, "s_batches")
@@ -94,6 +127,10 @@ class CellGrid:
         """Rows of ascending-(d2, index) neighbours, truncated/padded to ``width`` columns.
 
         Returns (idx [Nq,width], counts [Nq] or None, stats int32 [2] = {max count, status})."""
+        with _device_of(queries):
+            return self._query(queries, q_lens, radius, width, stats, want_counts, idx64, order)
+
+    def _query(self, queries, q_lens, radius, width, stats, want_counts, idx64, order):
         lib = _lib.load()
         queries = _f32c(queries, "queries")
         q_lens = _i32c(q_lens, "q_batches")
@@ -121,6 +158,7 @@ def _order_ptr(order: Optional[torch.Tensor], n_rows: int):
     return order.data_ptr()
 
 
+@_on_tensor_device
 def pack_rows(rows: torch.Tensor, out_width: int, idx64: bool) -> torch.Tensor:
     """[n, in_width] int32 -> [n, out_width] int32/int64 (kpreg_pack_rows)."""
     lib = _lib.load()
@@ -138,6 +176,7 @@ def pack_rows(rows: torch.Tensor, out_width: int, idx64: bool) -> torch.Tensor:
 # KPConv
 # ------------------------------------------------------------------------------------------------
 
+@_on_tensor_device
 def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: float, influence: str = "linear",
                    aggregation: str = "sum", gemm: int = 0, order: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
@@ -168,6 +207,7 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     return out
 
 
+@_on_tensor_device
 def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_extent: float,
                     influence: str = "linear", aggregation: str = "sum", order: Optional[torch.Tensor] = None):
     """Returns (d_x [n_s,c_in], d_weights [K,c_in,c_out])."""
@@ -196,6 +236,7 @@ def kpconv_backward(q_pts, s_pts, idx, x, weights, kernel_points, grad_out, kp_e
 # max pool
 # ------------------------------------------------------------------------------------------------
 
+@_on_tensor_device
 def max_pool_forward(x, idx, want_argmax: bool = False, order: Optional[torch.Tensor] = None):
     lib = _lib.load()
     x = _f32c(x, "x")
@@ -210,6 +251,7 @@ def max_pool_forward(x, idx, want_argmax: bool = False, order: Optional[torch.Te
     return out, arg
 
 
+@_on_tensor_device
 def max_pool_backward(grad_out, argmax, n_s: int):
     lib = _lib.load()
     grad_out = _f32c(grad_out, "grad_out")
@@ -225,6 +267,7 @@ def max_pool_backward(grad_out, argmax, n_s: int):
 # Kabsch
 # ------------------------------------------------------------------------------------------------
 
+@_on_tensor_device
 def kabsch(a: torch.Tensor, b: torch.Tensor, w: Optional[torch.Tensor], n_sets: int, pts_per_set: int,
            offsets: Optional[torch.Tensor] = None, threshold: float = -1.0, write_back: bool = False) -> torch.Tensor:
     """a, b [total,3] f32 (contiguous), w [total] f32 or None -> [n_sets,3,4] (kpreg_kabsch).
@@ -270,21 +313,53 @@ class SplitWeights:
         _lib.check(rc, "kpreg_split_weights")
 
 
-_SPLIT_CACHE: dict = {}
+# Inference caches (split weights here; folded Linear+BatchNorm weights, chain packs and joint conv3/downsample matrices
+# in res2net.py) are validated by tensor identity + Tensor._version + this epoch.  In-place updates through the autograd
+# API (optimizer steps, load_state_dict, copy_) bump _version; writes through ``.data`` (``p.data.copy_()``, hand-written
+# EMA updates, ``bn.running_var.data.fill_()``) do NOT — call ``invalidate_caches()`` after such writes.  The encoder's
+# modules call it themselves from train() / eval(), load_state_dict() and .to() / .cuda() / .float().
+_CACHE_EPOCH = [0]
+_SPLIT_CACHE = WeakIdKeyDictionary()  # weight tensor -> {transpose: (version, epoch, SplitWeights)}
+
+
+def cache_epoch() -> int:
+    return _CACHE_EPOCH[0]
+
+
+def invalidate_caches() -> None:
+    """Drop every cached derived weight (split TF32 operands, folded Linear+BatchNorm, chain packs).  Needed only after
+    parameter / running-statistic writes that bypass autograd's version counter (``.data`` writes)."""
+    _CACHE_EPOCH[0] += 1
+    _SPLIT_CACHE.clear()
+
+
+class CacheInvalidatingModule(torch.nn.Module):
+    """nn.Module whose mode switches, state-dict loads and device / dtype moves invalidate the inference caches."""
+
+    def train(self, mode: bool = True):
+        invalidate_caches()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        invalidate_caches()
+        return super()._load_from_state_dict(*args, **kwargs)
 
 
 def cached_split(weight: torch.Tensor, transpose: bool) -> SplitWeights:
-    """Split-weight cache for inference.  An entry is valid only for the very same tensor object (checked through
-    a weak reference, so a recycled address can never alias) at the same version counter (in-place updates by an
-    optimizer or load_state_dict bump it)."""
-    key = (id(weight), bool(transpose))
-    hit = _SPLIT_CACHE.get(key)
-    if hit is None or hit[0]() is not weight or hit[1] != weight._version:
-        if len(_SPLIT_CACHE) > 4096:
-            for k in [k for k, v in _SPLIT_CACHE.items() if v[0]() is None]:
-                del _SPLIT_CACHE[k]
-        hit = (weakref.ref(weight), weight._version, SplitWeights(weight, transpose))
-        _SPLIT_CACHE[key] = hit
+    """Split-weight cache for inference, keyed weakly by the weight tensor itself (a dead tensor's entry — and its
+    device buffer — disappears with it) and validated by its version counter and the cache epoch."""
+    per_tensor = _SPLIT_CACHE.get(weight)
+    if per_tensor is None:
+        per_tensor = {}
+        _SPLIT_CACHE[weight] = per_tensor
+    hit = per_tensor.get(bool(transpose))
+    if hit is None or hit[0] != weight._version or hit[1] != _CACHE_EPOCH[0]:
+        hit = (weight._version, _CACHE_EPOCH[0], SplitWeights(weight, transpose))
+        per_tensor[bool(transpose)] = hit
     return hit[2]
 
 
@@ -296,6 +371,7 @@ def _rows(t: torch.Tensor, name: str):
     return t, int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
 
 
+@_on_tensor_device
 def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act=None, slope: float = 0.1, out=None,
                    out2=None, addend=None, gemm: int = 1, post_residual=None, post_act=None):
     """act((x @ weight.T) * col_scale + col_shift + residual) -> out [M,N] (kpreg_linear_forward).
@@ -342,6 +418,7 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     return out
 
 
+@_on_tensor_device
 def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: float = 1e-5, out=None):
     """Per-cloud, per-channel (x - mean) * rstd (+ residual) (+ activation) (kpreg_segment_norm_forward)."""
     lib = _lib.load()
@@ -384,6 +461,7 @@ def chain_supported(width: int, n_layers: int) -> bool:
     return bool(_lib.load().kpreg_chain_supported(int(width), int(n_layers)))
 
 
+@_on_tensor_device
 def chain_forward(t: torch.Tensor, pack: ChainPack, z: torch.Tensor, x_copy: Optional[torch.Tensor] = None) -> torch.Tensor:
     """res2net's chained layers over conv1's output t [M, (L+1) w] into z [M, >= (L+1) w (+ c_x)] (kpreg_chain_forward)."""
     lib = _lib.load()

@@ -2,8 +2,10 @@
 
 Mirror of ``my_Bottle2neck`` / ``my_res2Net`` in the reference's ``models/backbone_kpconv/res2net.py``
 (:84-159, :231-265) with identical sub-module names (``layer1.0.conv1``, ``bn1``, ``convs.i``, ``bns.i``,
-``conv3``, ``bn3``, ``downsample.0/1``) so checkpoints are interchangeable.  These are small dense
-Linear + BatchNorm1d + ReLU layers on [N, C] tensors; they stay on stock PyTorch.
+``conv3``, ``bn3``, ``downsample.0/1``) so checkpoints are interchangeable.  In inference on CUDA (width a
+multiple of 4) the unit runs on the fused path (``_fused_forward``): Linear + eval-BatchNorm (+ ReLU) as tcgen05
+GEMMs with fused epilogues, the chained layers in one register-resident kernel; with autograd enabled or in training
+mode the layers are stock PyTorch ops.
 """
 from __future__ import annotations
 
@@ -13,12 +15,22 @@ import torch
 import torch.nn as nn
 
 
+def _cache_base():
+    from . import ops
+    return ops.CacheInvalidatingModule
+
+
+_CacheInvalidating = _cache_base()
+
+
 def _folded(linear: nn.Linear, bn: nn.BatchNorm1d):
     """(weight', shift) with the eval-mode BatchNorm1d folded into the bias-free Linear that precedes it:
     bn(x W^T) = x (diag(s) W)^T + (beta - mean * s),  s = gamma / sqrt(var + eps).
-    Cached on the BatchNorm module until a parameter or running statistic changes."""
+    Cached on the BatchNorm module until a parameter or running statistic changes (version counters) or
+    ``ops.invalidate_caches()`` is called (needed after writes through ``.data``, which bypass the counters)."""
+    from . import ops
     key = (linear.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
-           bn.running_var._version, linear.weight.data_ptr(), bn.running_mean.data_ptr())
+           bn.running_var._version, linear.weight.data_ptr(), bn.running_mean.data_ptr(), ops.cache_epoch())
     cache = getattr(bn, "_kpreg_folded", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
@@ -28,7 +40,7 @@ def _folded(linear: nn.Linear, bn: nn.BatchNorm1d):
     return cache[1], cache[2]
 
 
-class my_Bottle2neck(nn.Module):
+class my_Bottle2neck(_CacheInvalidating):
     """Linear(in -> w*s) -> split into s groups of width w; group i (i < s-1) is passed through its own
     Linear+BN+ReLU after adding the previous group's output (hierarchical residual); the last group is
     passed through unchanged; concat -> Linear(w*s -> planes) + BN, residual (optionally projected), ReLU."""
@@ -137,7 +149,7 @@ class my_Bottle2neck(nn.Module):
         return out if shortcut is None else torch.nn.functional.leaky_relu(out + shortcut, 0.1)
 
 
-class my_res2Net(nn.Module):
+class my_res2Net(_CacheInvalidating):
     """One ``block`` mapping in_dim -> out_dim channels, with a Linear+BN projection on the residual."""
 
     def __init__(self, block, in_dim, out_dim, baseWidth=26, scale=4):

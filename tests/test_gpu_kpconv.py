@@ -329,3 +329,36 @@ def test_row_positive_predicate_never_flips_on_encoder_features(oracle):
     record_parity("row_positive_predicate_sign_flips", flips, 0.5)
     record_parity("row_positive_predicate_closest_relative_sum", closest, float("inf"))
     assert flips == 0
+
+
+def test_fused_caches_follow_parameter_updates():
+    """The fused inference path caches derived weights (split TF32 operands, folded Linear+BatchNorm, chain packs).
+    Updates through the autograd API are seen through the version counters; writes through ``.data`` need
+    ``kpreg_b200.invalidate_caches()`` (documented in ops.py) — after it the fused path and stock PyTorch agree again."""
+    from kpreg_b200.res2net import my_Bottle2neck, my_res2Net
+    torch.manual_seed(3)
+    unit = my_res2Net(my_Bottle2neck, 32, 128, baseWidth=14, scale=8).cuda().eval()
+    x = torch.randn(5000, 32, device="cuda")
+
+    def both():
+        with torch.no_grad():
+            fused = unit(x)
+            kpconv_blocks.FUSED_GLUE = False
+            try:
+                stock = unit(x)
+            finally:
+                kpconv_blocks.FUSED_GLUE = True
+        return rel_err(fused.cpu().numpy(), stock.cpu().numpy())
+
+    assert both() < TOL
+    blk = unit.layer1[0]
+    with torch.no_grad():
+        blk.conv1.weight.mul_(1.5)                 # bumps the version counter: picked up without help
+        blk.bns[2].running_var.add_(0.3)
+    assert both() < TOL
+    blk.conv3.weight.data.mul_(0.5)                # .data writes bypass the counters ...
+    blk.bn1.running_mean.data.add_(0.25)
+    kpreg_b200.invalidate_caches()                 # ... so the caches are dropped explicitly
+    assert both() < TOL
+    unit.load_state_dict({k: v * 0.9 if v.is_floating_point() else v for k, v in unit.state_dict().items()})
+    assert both() < TOL
