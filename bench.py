@@ -169,7 +169,28 @@ def kpconv_work(meta, cfg):
 # CPU reference path (oracle): test/bench infrastructure, never the product
 # ------------------------------------------------------------------------------------------------------
 
+def _import_reference_encoder():
+    """The reference's own KPFEncoder class when /root/reference is present (the build container); None on the GPU box."""
+    if not os.path.isdir("/root/reference/models/backbone_kpconv"):
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        cwd = os.getcwd()
+        from make_golden import import_reference
+        fk, _, _ = import_reference()       # chdirs into the reference tree (its kernel dispositions are CWD-relative)
+        os.chdir(cwd)
+        return fk
+    except Exception as exc:  # noqa: BLE001
+        print(f"bench.py: reference import failed ({exc}); using the port", file=sys.stderr)
+        return None
+
+
 class CpuReference:
+    """The reference path on the host cores: preprocessing = the UNMODIFIED reference C++ (oracle/_ref) when it was built,
+    else the C port; encoder = the reference's own KPFEncoder when /root/reference is importable (build container), else the
+    torch-CPU port (oracle/kp_oracle.py); Kabsch = the port of compute_rigid_transform.  `kind` is "reference" only when
+    preprocessing AND encoder are the reference's own code."""
+
     def __init__(self, cfg, state_dict):
         import kp_oracle
         self.o = kp_oracle
@@ -179,6 +200,24 @@ class CpuReference:
         self.sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
+        self.ref_encoder = None
+        fk = _import_reference_encoder()
+        if fk is not None:
+            cwd = os.getcwd()
+            os.chdir("/root/reference")
+            try:
+                enc = fk.KPFEncoder(cfg, cfg.d_embed)
+                enc.load_state_dict(self.sd, strict=True)
+                self.ref_encoder = enc.eval()
+            finally:
+                os.chdir(cwd)
+        self.kind = "reference" if (self.impl == "ref" and self.ref_encoder is not None) else "port"
+
+    def describe(self):
+        pre = "unmodified reference C++ (oracle/_ref, 1 thread — it is single-threaded by construction)" if self.impl == "ref" else "C port (1 thread)"
+        enc = ("the reference's own KPFEncoder (imported from /root/reference)" if self.ref_encoder is not None
+               else "torch-CPU port of the reference's KPFEncoder (oracle/kp_oracle.py; /root/reference is absent on this box)")
+        return f"preprocess = {pre}; encoder = {enc} on {self.cores} threads; Kabsch = port of compute_rigid_transform"
 
     def pair(self, src, tgt, pose, seed=0):
         """One pair through preprocess -> encoder -> Kabsch on the host.  Returns stage seconds."""
@@ -188,13 +227,18 @@ class CpuReference:
         t1 = time.perf_counter()
         x0 = np.ones((meta["points"][0].shape[0], 1), np.float32)
         with torch.no_grad():
-            self.o.encoder_forward(self.sd, self.cfg, x0, meta)
+            if self.ref_encoder is not None:
+                batch = {k: [torch.from_numpy(np.ascontiguousarray(a)) for a in v] for k, v in meta.items()}
+                feats, _ = self.ref_encoder(torch.from_numpy(x0), batch)
+            else:
+                feats, _ = self.o.encoder_forward(self.sd, self.cfg, x0, meta)
         t2 = time.perf_counter()
         lens = [int(v) for v in meta["stack_lengths"][-1]]
         a, b, w = synthetic_correspondences(torch.from_numpy(meta["points"][-1]), lens, torch.from_numpy(pose)[None], seed=seed)
         t3 = time.perf_counter()
-        self.o.fast_compute_rigid_transform(a[0], b[0], w[0], 0.85)
+        pose_out = self.o.fast_compute_rigid_transform(a[0], b[0], w[0], 0.85)
         t4 = time.perf_counter()
+        self.last = {"meta": meta, "feats": feats, "pose": pose_out, "corr": (a[0], b[0], w[0])}
         return {"preprocess": t1 - t0, "encoder": t2 - t1, "kabsch": t4 - t3}
 
 
@@ -219,15 +263,12 @@ def run_reference_arm(args, rank, world):
         t_total += sum(st.values())
     value = args.steps / t_total
     split = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
-    kind = "reference" if ref.impl == "ref" else "port"
-    sample = (f"{args.steps} steps x 1 pair of the workload; preprocess = "
-              f"{'unmodified reference C++ (oracle/_ref, 1 thread)' if ref.impl == 'ref' else 'C port'}, "
-              f"encoder/Kabsch = torch-CPU restatement of the reference ops on {ref.cores} threads; "
+    sample = (f"{args.steps} steps x 1 pair of the workload; {ref.describe()}; "
               f"stage s/pair {json.dumps({k: round(v, 4) for k, v in split.items()})}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": 1},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -236,16 +277,107 @@ def run_reference_arm(args, rank, world):
 # our arm
 # ------------------------------------------------------------------------------------------------------
 
+def parity_check(ref, path, out, src_np, tgt_np, poses_np, n_pairs):
+    """After the timed region: pair 0 of the measured batch through the CPU reference path (the checker), compared with the
+    rows of the GPU batch that belong to that pair — pyramid points bit-exact, encoder features <= 1e-4 (max-norm), pose
+    <= 1e-3 deg / 1e-5 m on the same correspondences."""
+    import kp_oracle
+    ref.pair(src_np[0], tgt_np[0], poses_np[0])
+    want = ref.last
+    meta = out["meta"]
+    points_equal, feat_err = True, None
+    for lvl, pts in enumerate(meta["points"]):
+        lens = meta["stack_lengths"][lvl].cpu().numpy().astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        rows = np.concatenate([np.arange(offs[0], offs[1]), np.arange(offs[n_pairs], offs[n_pairs + 1])])
+        got = pts[torch.from_numpy(rows).to(pts.device)].cpu().numpy()
+        points_equal = points_equal and got.shape == want["meta"]["points"][lvl].shape and bool(np.array_equal(got, want["meta"]["points"][lvl]))
+        if lvl == len(meta["points"]) - 1:
+            f = out["feats"][torch.from_numpy(rows).to(pts.device)].cpu().numpy()
+            w = want["feats"].numpy()
+            feat_err = float(np.abs(f - w).max() / max(np.abs(w).max(), 1e-30)) if f.shape == w.shape else float("inf")
+    # pose: the GPU Kabsch on pair 0's correspondences of the batch vs the port on the same numbers
+    a, b, w, offsets = out["corr"]
+    lo, hi = int(offsets[0]), int(offsets[6])
+    n_c = (hi - lo) // 6
+    t_ref = kp_oracle.fast_compute_rigid_transform(a[lo:hi].reshape(6, n_c, 3).cpu(), b[lo:hi].reshape(6, n_c, 3).cpu(),
+                                                   w[lo:hi].reshape(6, n_c).cpu(), 0.85)
+    perr = kp_oracle.pose_error(out["poses"][:, 0].cpu(), t_ref)
+    rot, trans = float(perr["rot_deg"].max()), float(perr["trans"].max())
+    ok = bool(points_equal and feat_err is not None and feat_err < 1e-4 and rot < 1e-3 and trans < 1e-5)
+    return {"pair": 0, "checker": ref.kind, "points_bit_exact": points_equal, "feature_rel_err": feat_err, "feature_bound": 1e-4,
+            "pose_rot_deg_err": rot, "pose_trans_err": trans, "ok": ok}
+
+
+def other_configs(dev, steps=5):
+    """BASELINE configs 1, 3 and 4 (N = 1): single-pair latency of the ModelNet and MCD shapes through pyramid + encoder +
+    Kabsch, and the 8-pair training step (forward + backward through the encoder).  Device-timed with CUDA events."""
+    import kpreg_b200  # noqa: F401
+    from kpreg_b200 import kpconv_config, synthetic
+    from kpreg_b200.kpconv import KPFEncoder, Preprocessor
+    from kpreg_b200.pipeline import RegistrationPath
+    res = {}
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    for name, gen in (("modelnet", synthetic.modelnet_pair), ("mcd", synthetic.mcd_pair)):
+        cfg = kpconv_config(name)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        path = RegistrationPath(cfg, index_dtype=torch.int32, weights_threshold=0.85).eval().to(dev)
+        src, tgt, pose = gen(seed=7)
+        s, t, p = [torch.from_numpy(src).to(dev)], [torch.from_numpy(tgt).to(dev)], torch.from_numpy(pose)[None].to(dev)
+        out = path(s, t, p)
+        ms = timed(lambda: path(s, t, p), steps)
+        res[f"{name}_single_pair"] = {"ms_per_pair": ms, "pairs_per_s": 1000.0 / ms,
+                                      "points_per_level": [int(x.shape[0]) for x in out["meta"]["points"]],
+                                      "neighbor_widths": [int(x.shape[1]) for x in out["meta"]["neighbors"]]}
+        del path, out
+    cfg = kpconv_config("3dmatch")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    pairs = [synthetic.threedmatch_pair(seed=100 + i) for i in range(8)]
+    pts = [torch.from_numpy(p[0]).to(dev) for p in pairs] + [torch.from_numpy(p[1]).to(dev) for p in pairs]
+    pre = Preprocessor(cfg, index_dtype=torch.int32)
+    enc = KPFEncoder(cfg, cfg.d_embed).train().to(dev)
+    meta = pre(pts)
+    x0 = torch.ones((meta["points"][0].shape[0], 1), device=dev)
+
+    def train_step():
+        enc.zero_grad(set_to_none=True)
+        y, _ = enc(x0, meta)
+        y.square().mean().backward()
+
+    ms = timed(train_step, 3)
+    res["train_step_8_pairs"] = {"ms_per_step": ms, "pairs_per_s": 8000.0 / ms,
+                                 "what": "forward + backward through all 11 KPConv ops and 3 max_pools of the encoder (BatchNorm in training mode), pyramid precomputed"}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per (sub-)batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --pairs per GPU per step; strong: --global-pairs per step sharded round-robin over the GPUs (SURVEY §8d config 5)")
+    ap.add_argument("--global-pairs", type=int, default=512)
     ap.add_argument("--gemm", type=int, default=None, help="contractions: 0 fp32 CUDA cores, 1 tcgen05 3xTF32 (default)")
     ap.add_argument("--no-fused-glue", action="store_true", help="run the block glue on stock PyTorch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the ModelNet / MCD / training-step side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -260,16 +392,16 @@ def main():
     import torch.distributed as dist
     import kpreg_b200  # noqa: F401
     from kpreg_b200 import _lib, kpconv_blocks, kpconv_config
-    from kpreg_b200.pipeline import RegistrationPath, gather_results, result_rows
+    from kpreg_b200.pipeline import RegistrationPath, gather_results, result_rows, shard_pairs
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 must print exactly one JSON line on stdout: keep NCCL's own banner ("NCCL version ...") off it
-        if "KPREG_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "NONE"
+        # rank 0 prints exactly one JSON line on stdout: NCCL's own log lines (banner, NCCL_DEBUG=INFO topology / rank lines)
+        # go to stderr instead of being silenced, so that they can still be read
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if args.gemm is not None:
         kpconv_blocks.DEFAULT_GEMM = args.gemm
@@ -281,29 +413,67 @@ def main():
     np.random.seed(0)
     path = RegistrationPath(cfg, index_dtype=torch.int32, weights_threshold=0.85).eval().to(dev)
 
-    # weak scaling: every rank gets its own P pairs (global pair g = rank + world * local index)
-    src_np, tgt_np, poses_np = make_pairs(args.pairs, 1000 + 100 * rank)
-    src_host = [torch.from_numpy(a).pin_memory() for a in src_np]
-    tgt_host = [torch.from_numpy(a).pin_memory() for a in tgt_np]
-    poses_host = torch.from_numpy(poses_np).pin_memory()
-    src_dev = [a.to(dev) for a in src_host]
-    tgt_dev = [a.to(dev) for a in tgt_host]
-    poses_dev = poses_host.to(dev)
-    h2d_bytes = sum(a.numel() * 4 for a in src_host + tgt_host) + poses_host.numel() * 4
-    n_global = args.pairs * world
+    # the step's pairs of this rank, as sub-batches of at most --pairs pairs
+    if args.scaling == "weak":
+        n_global = args.pairs * world                      # every rank gets its own P pairs (global pair = rank + world * i)
+        src_np, tgt_np, poses_np = make_pairs(args.pairs, 1000 + 100 * rank)
+        my_batches = [list(range(args.pairs))]
+    else:
+        n_global = args.global_pairs                       # fixed global set, pair g -> rank g mod world
+        n_unique = min(n_global, 64)                       # (64 distinct synthetic pairs, cycled: generation is host time)
+        src_np, tgt_np, poses_np = make_pairs(n_unique, 1000)
+        mine = [g % n_unique for g in shard_pairs(n_global, rank, world)]
+        my_batches = [mine[i:i + args.pairs] for i in range(0, len(mine), args.pairs)]
+    n_local = sum(len(b) for b in my_batches)
+
+    class Batch:
+        """One sub-batch: clouds resident on the device, and the same clouds in ONE pinned host buffer (a single
+        host-to-device copy per sub-batch in the end-to-end measurement)."""
+
+        def __init__(self, ids):
+            self.n = len(ids)
+            clouds = [src_np[i] for i in ids] + [tgt_np[i] for i in ids]
+            self.lens = [int(c.shape[0]) for c in clouds]
+            self.host = torch.from_numpy(np.concatenate(clouds, 0)).pin_memory()
+            self.poses_host = torch.from_numpy(np.stack([poses_np[i] for i in ids])).pin_memory()
+            dev_all = self.host.to(dev)
+            parts = list(torch.split(dev_all, self.lens))
+            self.src_dev, self.tgt_dev = parts[:self.n], parts[self.n:]
+            self.poses_dev = self.poses_host.to(dev)
+            self.h2d_bytes = self.host.numel() * 4 + self.poses_host.numel() * 4
+            # decoder-shaped correspondences: in the model they are the decoder's output; the synthetic stand-ins are built
+            # once, outside the timed region, from this batch's own coarse level
+            self.corr = path(self.src_dev, self.tgt_dev, self.poses_dev)["corr"]
+
+    batches = [Batch(ids) for ids in my_batches]
+    h2d_bytes = sum(b.h2d_bytes for b in batches)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    def finish(rows_list, last_out):
+        rows = torch.cat(rows_list, 0) if len(rows_list) > 1 else rows_list[0]
+        if args.scaling == "strong" and world > 1:
+            per = (n_global + world - 1) // world
+            padded = torch.zeros((per, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            padded[:rows.shape[0]] = rows
+            table = torch.empty((world * per, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            dist.all_gather_into_tensor(table, padded)
+            return table, last_out
+        return gather_results(rows, n_local * world, rank, world), last_out
+
     def step_resident():
-        out = path(src_dev, tgt_dev, poses_dev)
-        rows = result_rows(out)
-        return gather_results(rows, n_global, rank, world), out
+        rows, out = [], None
+        for b in batches:
+            out = path(b.src_dev, b.tgt_dev, b.poses_dev, corr=b.corr)
+            rows.append(result_rows(out))
+        return finish(rows, out)
 
     def step_e2e():
-        s = [a.to(dev, non_blocking=True) for a in src_host]
-        t = [a.to(dev, non_blocking=True) for a in tgt_host]
-        p = poses_host.to(dev, non_blocking=True)
-        out = path(s, t, p)
-        table = gather_results(result_rows(out), n_global, rank, world)
+        rows, out = [], None
+        for b in batches:
+            parts = list(torch.split(b.host.to(dev, non_blocking=True), b.lens))   # ONE copy of the sub-batch's clouds
+            out = path(parts[:b.n], parts[b.n:], b.poses_host.to(dev, non_blocking=True), corr=b.corr)
+            rows.append(result_rows(out))
+        table, out = finish(rows, out)
         return table.cpu(), out  # D2H of every pair's pose + errors
 
     def timed(fn, steps, warmup, profile):
@@ -345,7 +515,8 @@ def main():
     ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
     while time.perf_counter() - t_ramp < ramp_s:
         # local work only: the iteration count is time-based and differs per rank, so NO collective in here
-        path(src_dev, tgt_dev, poses_dev)
+        b0 = batches[0]
+        path(b0.src_dev, b0.tgt_dev, b0.poses_dev, corr=b0.corr)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -355,21 +526,22 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_e2e, _, _, last_e2e = timed(step_e2e, args.steps, args.warmup, profile=False)
 
-    value = n_global * args.steps / (ms_total / 1000.0)
-    e2e_value = n_global * args.steps / (ms_e2e / 1000.0)
+    value = n_global * args.steps / (ms_total / 1000.0) if args.scaling == "strong" else n_local * world * args.steps / (ms_total / 1000.0)
+    e2e_value = value * ms_total / ms_e2e
     table, out = last
     d2h_bytes = int(last_e2e[0].numel() * 4)
 
     if rank == 0:
         pk = peaks()
-        work = kpconv_work(out["meta"], cfg)
+        scale_work = n_local / batches[-1].n       # the families' times cover every sub-batch; the work formulas the last one
+        work = {k: v * scale_work for k, v in kpconv_work(out["meta"], cfg).items()}
         fam_ms = {k: v[0] / args.steps for k, v in fam.items()}
         fam_n = {k: v[1] / args.steps for k, v in fam.items()}
         top = max(("kpconv_gather", "kpconv_contract", "grid_query", "subsample", "linear"), key=lambda k: fam_ms[k])
         nbytes = {"kpconv_gather": work["kpconv_bytes"], "grid_query": work["query_bytes"], "subsample": work["subsample_bytes"],
                   "linear": work["linear_bytes"], "kpconv_contract": None}[top]
-        names = {"kpconv_gather": "k_kpconv_gather (KPConv gather + influence + aggregation)",
-                 "grid_query": "k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
+        names = {"kpconv_gather": "k_kpconv_gather_mma + k_kpconv_c1 (KPConv gather + influence + aggregation)",
+                 "grid_query": "k_grid_query_tq / k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
                  "linear": "k_gemm_tc + k_chain (block Linear layers: tcgen05 3xTF32 GEMMs, register-resident res2net chain)",
                  "kpconv_contract": "k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 3xTF32)"}
         if top == "kpconv_contract":
@@ -380,8 +552,13 @@ def main():
             ach = nbytes / (fam_ms[top] * 1e-3) / 1e9
             roof = {"kernel": names[top], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None}
-        # every family against its own bound, for the record
-        roof["families"] = {
+        # every family against its own bound, for the record (TF32 peak: profiles/r2_tf32_peak.json, cuBLAS 8192^3 on this pool)
+        tf32 = None
+        tpk = os.path.join(ROOT, "profiles", "r2_tf32_peak.json")
+        if os.path.exists(tpk):
+            tf32 = json.load(open(tpk)).get("tf32_tflops_sustained")
+        hbm = pk["hbm_gbs"]
+        fams = {
             "kpconv_gather_GBs": work["kpconv_bytes"] / (fam_ms["kpconv_gather"] * 1e-3) / 1e9,
             "kpconv_gather_fp32_TFLOPs": work["gather_flops"] / (fam_ms["kpconv_gather"] * 1e-3) / 1e12,
             "kpconv_contract_TFLOPs": work["contract_flops"] / max(fam_ms["kpconv_contract"], 1e-9) / 1e9,
@@ -389,64 +566,82 @@ def main():
             "linear_TFLOPs": work["linear_flops"] / max(fam_ms["linear"], 1e-9) / 1e9,
             "grid_query_GBs": work["query_bytes"] / max(fam_ms["grid_query"], 1e-9) / 1e6,
             "segment_norm_GBs": work["segment_norm_bytes"] / max(fam_ms["segment_norm"], 1e-9) / 1e6,
+            "subsample_GBs": work["subsample_bytes"] / max(fam_ms["subsample"], 1e-9) / 1e6,
         }
-        # DRAM traffic of the family from the committed ncu capture (profiles/r1g_dram_traffic.json: dram__bytes_read.sum +
-        # dram__bytes_write.sum over one step's launches), scaled to this run's pairs per step
-        tpath = os.path.join(ROOT, "profiles", "r1g_dram_traffic.json")
+        fams["frac_of_hbm"] = {k[:-4]: round(fams[k] / hbm, 4) for k in ("kpconv_gather_GBs", "linear_GBs", "grid_query_GBs", "segment_norm_GBs", "subsample_GBs")}
+        if tf32:
+            # 3xTF32: three tensor-core products per fp32-equivalent product
+            fams["kpconv_contract_frac_of_tf32_peak"] = {"fp32_equivalent": round(fams["kpconv_contract_TFLOPs"] / tf32, 4),
+                                                          "issued_3x": round(3 * fams["kpconv_contract_TFLOPs"] / tf32, 4), "tf32_peak_TFLOPs": tf32}
+        roof["families"] = fams
+        # DRAM traffic of the family from the committed ncu capture of this build (dram__bytes_read.sum + dram__bytes_write.sum
+        # over one step's launches), scaled to this run's pairs per step
+        tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
         fam_kernels = {"linear": ("k_gemm_tc", "k_chain"), "kpconv_contract": ("k_gemm_tc",),
                        "kpconv_gather": ("k_kpconv_gather_mma", "k_kpconv_c1"), "grid_query": ("k_grid_query",)}.get(top)
         if os.path.exists(tpath) and fam_kernels:
             tr = json.load(open(tpath))
             fs = [tr["families"][k] for k in fam_kernels if k in tr["families"]]
             if fs:
-                roof["traffic"] = sum(f["dram_read_MB"] + f["dram_write_MB"] for f in fs) * 1e6 * args.pairs / tr["pairs"]
-                roof["traffic_note"] = (f"bytes per step, all {' + '.join(fam_kernels)} launches (ncu capture at {tr['pairs']} pairs/step "
-                                        f"scaled to {args.pairs}; k_gemm_tc also serves the KPConv contraction); achieved / algorithmic "
-                                        "figures are per step as well")
+                roof["traffic"] = sum(f["dram_read_MB"] + f["dram_write_MB"] for f in fs) * 1e6 * n_local / tr["pairs"]
+                roof["traffic_note"] = (f"bytes per step, all {' + '.join(fam_kernels)} launches (ncu capture at {tr['pairs']} pairs/step, "
+                                        f"profiles/r2_dram_traffic.json, scaled to {n_local}; k_gemm_tc also serves the KPConv contraction); "
+                                        "achieved / algorithmic figures are per step as well")
         if roof["traffic"] is None:
-            roof["traffic_note"] = ("no ncu DRAM capture of this build is committed (the round's last launch list was lost to the 64 MiB "
-                                    "copy-back limit); profiles/r1d_dram_traffic.json holds the previous build's: 82 GB per 64-pair step "
-                                    "for all k_gemm_tc launches against 88 GB algorithmic")
+            roof["traffic_note"] = "profiles/r2_dram_traffic.json is missing"
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
         roof["share_of_step"] = round(fam_ms[top] / (ms_total / args.steps), 4)
+        roof["untimed_residue_ms"] = round(ms_total / args.steps - sum(fam_ms.values()), 4)
         roof["algorithmic_per_step"] = work
 
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(cfg, path.kpf_encoder.state_dict())
-            ref.pair(src_np[0], tgt_np[0], poses_np[0])  # warm-up
+            ids = my_batches[-1]
+            parity = parity_check(ref, path, out, [src_np[i] for i in ids], [tgt_np[i] for i in ids], [poses_np[i] for i in ids], len(ids))
             n_s, t_s, stages = 2, 0.0, []
             for i in range(n_s):
-                st = ref.pair(src_np[i % args.pairs], tgt_np[i % args.pairs], poses_np[i % args.pairs])
+                j = ids[i % len(ids)]
+                st = ref.pair(src_np[j], tgt_np[j], poses_np[j])
                 stages.append(st)
                 t_s += sum(st.values())
             split = {k: round(float(np.mean([s[k] for s in stages])), 4) for k in stages[0]}
-            cpu = {"value": n_s / t_s, "unit": UNIT, "cores": ref.cores, "kind": "reference" if ref.impl == "ref" else "port",
-                   "sample": f"{n_s} pairs of the same workload after 1 warm-up pair; preprocess on the "
-                             f"{'unmodified reference C++ (oracle/_ref)' if ref.impl == 'ref' else 'C port'} (1 thread), encoder + "
-                             f"Kabsch = torch-CPU restatement on {ref.cores} threads; stage s/pair {json.dumps(split)}"}
+            cpu = {"value": n_s / t_s, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                   "sample": f"{n_s} pairs of the same workload after 1 warm-up pair (the parity check's); {ref.describe()}; "
+                             f"stage s/pair {json.dumps(split)}"}
+        extra = None
+        if world == 1 and not args.no_other_configs:
+            del batches
+            torch.cuda.empty_cache()
+            extra = other_configs(dev)
 
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "global_pairs_per_step": n_global,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n_local, "global_pairs_per_step": n_global if args.scaling == "strong" else n_local * world,
+                       "sub_batch_pairs": args.pairs,
                        "points_per_level": [int(p.shape[0]) for p in out["meta"]["points"]],
                        "neighbor_widths": [int(t.shape[1]) for t in out["meta"]["neighbors"]],
                        "kpconv_contraction": "tcgen05-3xTF32" if kpconv_blocks.DEFAULT_GEMM == 1 else "fp32-cuda-core",
                        "block_glue": "fused CUDA (tcgen05 linear + segment norm)" if kpconv_blocks.FUSED_GLUE else "PyTorch ops",
-                       "parallelism": f"pairs sharded over {world} GPU(s); all-gather of [P,14] poses+errors",
+                       "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective; all-gather of [P,14] poses+errors per step",
+                       "kabsch_inputs": "decoder-shaped synthetic correspondences (the decoder is out of scope), built once from the batch's "
+                                        "own coarse level outside the timed region and resident on the device",
                        "l2": "256 MiB write between timed steps (outside the CUDA events)",
                        "ramp_up": "2 s of untimed steps before the W warm-up steps (fresh-box clocks / allocator)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_copies_per_step": 2 * len(my_batches)},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
-            "final_layer_pose_error": {"rot_deg_max": float(table[:, 12].max()), "trans_max": float(table[:, 13].max())},
+            "parity_check": parity,
+            "other_configs": extra,
+            "final_layer_pose_error": {"rot_deg_max": float(table[:, 12].max()), "trans_max": float(table[:, 13].max()),
+                                       "note": "against the generating pose through 1 cm synthetic correspondence noise — not a parity figure"},
         }
         print(json.dumps(line))
     if world > 1:

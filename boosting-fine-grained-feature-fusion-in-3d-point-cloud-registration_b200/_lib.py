@@ -60,6 +60,13 @@ _SIGNATURES = {
     "kpreg_chain_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr, _c_int, _c_int,
                                      _c_ptr]),
     "kpreg_kabsch": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f32, _c_int, _c_ptr, _c_ptr]),
+    "kpreg_overlap_pool": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_ptr, _c_ptr]),
+    "kpreg_sine_embed": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_f32, _c_ptr, _c_ptr, _c_ptr]),
+    "kpreg_pack_coarse_workspace_bytes": (_c_int, [_c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_pack_coarse": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
+                                   _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_shuffle_gather": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "kpreg_remap_pairs": (_c_int, [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_ptr, _c_ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -205,15 +205,13 @@ batch_neighbors_kpconv_gpu = batch_neighbors_kpconv
 def compute_overlaps(batch):
     """Ground-truth overlap ratio per point and pyramid level (reference :545-571): level 0 is the given
     per-point overlap mask; each further level averages the previous one over the valid entries of its pooling
-    rows.  One masked gather-mean per level, on whatever device the tables live."""
+    rows (kpreg_overlap_pool: one masked gather-mean kernel per level, on the device the tables live on)."""
     meta = batch['kpconv_meta']
-    level = torch.cat(batch['src_overlap'] + batch['tgt_overlap'], dim=0).type(torch.float)
+    dev = meta['points'][0].device
+    level = torch.cat([o.to(dev) for o in batch['src_overlap'] + batch['tgt_overlap']], dim=0).type(torch.float)
     pyramid = {'pyr_0': level}
     for p in range(1, len(meta['points'])):
-        pools = meta['pools'][p - 1].long()
-        valid = pools < level.shape[0]          # the pad value is the row count of the level below
-        gathered = level[pools.clamp(max=level.shape[0] - 1)] * valid
-        level = torch.clamp(gathered.sum(1) / valid.sum(1), min=0, max=1)
+        level = ops.overlap_pool(level, meta['pools'][p - 1])
         pyramid[f'pyr_{p}'] = level
     return pyramid
 

@@ -478,3 +478,110 @@ def chain_forward(t: torch.Tensor, pack: ChainPack, z: torch.Tensor, x_copy: Opt
                                  int(z.stride(0)) if m > 1 else int(z.shape[1]), x_ptr, ld_x, c_x, _lib.stream_ptr(t.device))
     _lib.check(rc, "kpreg_chain_forward")
     return z
+
+
+# ------------------------------------------------------------------------------------------------
+# the steps on either side of the path: overlap pyramid, coarse-level packing, point shuffling
+# ------------------------------------------------------------------------------------------------
+
+@_on_tensor_device
+def overlap_pool(level: torch.Tensor, pools: torch.Tensor) -> torch.Tensor:
+    """One level of compute_overlaps: clamp(mean of level over the valid entries of each pooling row, 0, 1)."""
+    lib = _lib.load()
+    level = _f32c(level, "overlap level")
+    idx, idx64 = _idx(pools, "pools")
+    n_q, h = idx.shape
+    out = torch.empty(n_q, dtype=torch.float32, device=level.device)
+    rc = lib.kpreg_overlap_pool(level.data_ptr(), idx.data_ptr(), idx64, n_q, int(level.shape[0]), h, out.data_ptr(),
+                                _lib.stream_ptr(level.device))
+    _lib.check(rc, "kpreg_overlap_pool")
+    return out
+
+
+@_on_tensor_device
+def sine_embed(xyz: torch.Tensor, d_model: int, num_feats: int, scale: float, dim_t: torch.Tensor) -> torch.Tensor:
+    """[..., n_dim] points -> [..., d_model] sine / cosine position code (kpreg_sine_embed)."""
+    lib = _lib.load()
+    _lib.require_cuda(xyz, "xyz")
+    flat = xyz.detach().to(torch.float32).reshape(-1, xyz.shape[-1]).contiguous()
+    out = torch.empty((flat.shape[0], d_model), dtype=torch.float32, device=flat.device)
+    rc = lib.kpreg_sine_embed(flat.data_ptr(), int(flat.shape[0]), int(flat.shape[1]), int(d_model), int(num_feats), float(scale),
+                              _f32c(dim_t, "dim_t").data_ptr(), out.data_ptr(), _lib.stream_ptr(flat.device))
+    _lib.check(rc, "kpreg_sine_embed")
+    return out.reshape(*xyz.shape[:-1], d_model)
+
+
+@_on_tensor_device
+def pack_coarse(feats: Optional[torch.Tensor], xyz: Optional[torch.Tensor], lens: torch.Tensor, max_len, d_model: int,
+                num_feats: int = 0, scale: float = 1.0, dim_t: Optional[torch.Tensor] = None):
+    """Padded (features, position embedding, padding masks) of the two halves of a stacked coarse level
+    (kpreg_pack_coarse).  Returns (src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask); the feature / embedding
+    entries are None when ``feats`` / ``xyz`` is None."""
+    lib = _lib.load()
+    lens = _i32c(lens, "stack_lengths")
+    n_pairs = int(lens.shape[0]) // 2
+    dev = lens.device
+    ns_max, nt_max = int(max_len[0]), int(max_len[1])
+    ld_f = 0
+    if feats is not None:
+        feats, ld_f = _rows(feats, "feats")
+        if feats.shape[1] != d_model:
+            raise RuntimeError("pack_coarse: feats must have d_model columns")
+    if xyz is not None:
+        xyz = _f32c(xyz, "xyz")
+
+    def buf(n_max, on):
+        return torch.empty((n_max, n_pairs, d_model), dtype=torch.float32, device=dev) if on else None
+
+    src_f, tgt_f = buf(ns_max, feats is not None), buf(nt_max, feats is not None)
+    src_pe, tgt_pe = buf(ns_max, xyz is not None), buf(nt_max, xyz is not None)
+    src_m = torch.empty((n_pairs, ns_max), dtype=torch.bool, device=dev)
+    tgt_m = torch.empty((n_pairs, nt_max), dtype=torch.bool, device=dev)
+    nbytes = _lib.size_query("kpreg_pack_coarse_workspace_bytes", n_pairs)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_pack_coarse(_lib.ptr(feats), ld_f, _lib.ptr(xyz), lens.data_ptr(), n_pairs, int(d_model), int(num_feats),
+                               float(scale), _lib.ptr(None if dim_t is None else _f32c(dim_t, "dim_t")), ns_max, nt_max,
+                               _lib.ptr(src_f), _lib.ptr(tgt_f), _lib.ptr(src_pe), _lib.ptr(tgt_pe), src_m.data_ptr(),
+                               tgt_m.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_pack_coarse")
+    return src_f, tgt_f, src_pe, tgt_pe, src_m, tgt_m
+
+
+@_on_tensor_device
+def shuffle_gather(pts: torch.Tensor, mask: Optional[torch.Tensor], perm: torch.Tensor, want_reverse: bool = False):
+    """(pts[perm], mask[perm] or None, reverse index int64 [n_in] or None, status int32 [1]) — kpreg_shuffle_gather."""
+    lib = _lib.load()
+    pts = _f32c(pts, "points")
+    _lib.require_cuda(perm, "perm")
+    perm = perm.to(torch.int64).contiguous()
+    n_in, n_out = int(pts.shape[0]), int(perm.shape[0])
+    dev = pts.device
+    out = torch.empty((n_out, 3), dtype=torch.float32, device=dev)
+    m_in = m_out = None
+    if mask is not None:
+        _lib.require_cuda(mask, "mask")
+        m_in = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+        m_out = torch.empty(n_out, dtype=torch.uint8, device=dev)
+    rev = torch.empty(n_in, dtype=torch.int64, device=dev) if want_reverse else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.kpreg_shuffle_gather(pts.data_ptr(), _lib.ptr(m_in), perm.data_ptr(), n_out, n_in, out.data_ptr(), _lib.ptr(m_out),
+                                  _lib.ptr(rev), status.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_shuffle_gather")
+    if m_out is not None and mask.dtype == torch.bool:
+        m_out = m_out.view(torch.bool)
+    return out, m_out, rev, status
+
+
+@_on_tensor_device
+def remap_pairs(corr: torch.Tensor, rev_src: torch.Tensor, rev_tgt: torch.Tensor):
+    """Correspondences [2, P] through two reverse indices -> (remapped [2, P] int64, keep [P] bool)."""
+    lib = _lib.load()
+    _lib.require_cuda(corr, "correspondences")
+    corr = corr.to(torch.int64).contiguous()
+    n = int(corr.shape[1])
+    out = torch.empty_like(corr)
+    keep = torch.empty(n, dtype=torch.bool, device=corr.device)
+    rc = lib.kpreg_remap_pairs(corr.data_ptr(), n, rev_src.data_ptr(), int(rev_src.shape[0]), rev_tgt.data_ptr(),
+                               int(rev_tgt.shape[0]), out.data_ptr(), keep.data_ptr(), _lib.stream_ptr(corr.device))
+    _lib.check(rc, "kpreg_remap_pairs")
+    return out, keep

@@ -130,17 +130,24 @@ class RegistrationPath(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, src_xyz: Sequence[torch.Tensor], tgt_xyz: Sequence[torch.Tensor], poses_gt: torch.Tensor,
-                corr_seed: int = 0) -> Dict[str, torch.Tensor]:
+                corr_seed: int = 0, corr=None) -> Dict[str, torch.Tensor]:
         """src_xyz / tgt_xyz: lists of [N_i,3] clouds (the batch dict of collate_pair,
         data_loaders/collate_functions.py:13-22); poses_gt [B,3,4] seeds the synthetic correspondences.
-        Returns the encoder features, the per-layer poses [6,B,3,4] and the final-layer pose errors."""
+        ``corr`` = (a, b, w, offsets) as returned in the result's 'corr' entry: decoder-shaped correspondences prepared
+        by the caller (in the model they are the decoder's output; building the synthetic stand-ins is not part of the
+        path).  Returns the encoder features, the per-layer poses [6,B,3,4] and the final-layer pose errors."""
         n_pairs = len(src_xyz)
         meta = self.preprocessor(list(src_xyz) + list(tgt_xyz))
         feats0 = torch.ones((meta['points'][0].shape[0], 1), dtype=torch.float32, device=meta['points'][0].device)
         feats, _ = self.kpf_encoder(feats0, meta)
         coarse = meta['points'][-1]
         poses_dev = poses_gt.to(coarse.device)
-        a, b, w, offsets = synthetic_correspondences_batched(coarse, meta['stack_lengths'][-1], poses_dev, seed=corr_seed)
+        if corr is not None:
+            a, b, w, offsets = corr
+            if int(a.shape[0]) != N_DECODER_LAYERS * int(coarse.shape[0]):
+                raise RuntimeError("corr does not match this batch's coarse level")
+        else:
+            a, b, w, offsets = synthetic_correspondences_batched(coarse, meta['stack_lengths'][-1], poses_dev, seed=corr_seed)
         thr = -1.0 if self.weights_threshold is None else float(self.weights_threshold)
         poses = ops.kabsch(a, b, w, n_pairs * N_DECODER_LAYERS, 0, offsets, thr, False)
         poses = poses.reshape(n_pairs, N_DECODER_LAYERS, 3, 4).transpose(0, 1).contiguous()   # [6, B, 3, 4]

@@ -226,6 +226,46 @@ KPREG_API int kpreg_chain_pack(const float* weights, const float* shifts, int wi
 KPREG_API int kpreg_chain_forward(const float* t, int ld_t, const void* pack, int width, int n_layers, int64_t m_rows,
                                   float* z, int ld_z, const float* x_copy, int ld_x, int c_x, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The steps on either side of the path.
+ *
+ * kpreg_overlap_pool: one level of compute_overlaps()   models/backbone_kpconv/finegrained_kpconv.py:545-571
+ *   out[n] = clamp(mean of level[idx[n,h]] over the entries with idx[n,h] < n_s, 0, 1); a row without a valid entry
+ *   is 0/0 = NaN, as in the reference.  level [n_s] f32, idx [n_q, n_nbrs] (the pyramid's `pools` table), out [n_q].
+ *
+ * kpreg_sine_embed: PositionEmbeddingCoordsSine.forward()   models/transformer/position_embedding.py:29-49
+ *   out[r, d*F + k] = (k even ? sin : cos)(xyz[r,d] * scale / dim_t[k]), columns >= n_dim*F zero.  dim_t [F] is the
+ *   reference's `temperature ** (2 * (k // 2) / F)` evaluated by the host in fp32 (same torch expression).
+ *
+ * kpreg_pack_coarse: split_src_tgt() + pad_sequence(..., require_padding_mask=True) of the projected coarse features AND
+ *   of their position embedding   utils/seq_manipulation.py:6-48, models/finegrained_regtr.py:149-172
+ *   feats [N, ld_f] (N = sum of lens; the first n_pairs clouds are sources, the last n_pairs targets), xyz [N,3],
+ *   lens int32 [2*n_pairs] on the device.  src_feats / src_pe [ns_max, n_pairs, d_model], tgt_* [nt_max, n_pairs,
+ *   d_model] (zero padded), src_mask [n_pairs, ns_max] / tgt_mask [n_pairs, nt_max] bytes, 1 at padded positions.
+ *   Any output pointer may be NULL.  workspace: kpreg_pack_coarse_workspace_bytes(n_pairs).
+ *
+ * kpreg_shuffle_gather / kpreg_remap_pairs: ShufflePoints.__call__()   data_loaders/transforms.py:95-131
+ *   out_pts[i] = pts[perm[i]], out_mask[i] = mask[perm[i]] (mask may be NULL), rev[perm[i]] = i and -1 elsewhere
+ *   (rev [n_in] int64, may be NULL); perm int64 [n_out] — the host's permutation, truncated to max_pts.  status
+ *   (int32 on the device) receives KPREG_E_RANGE if perm holds an index outside [0, n_in).
+ *   kpreg_remap_pairs maps correspondences corr [2, n_pairs] int64 through the two reverse indices into out [2,
+ *   n_pairs] and sets keep[p] = 1 where both survive; the caller compacts the kept columns in order.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_overlap_pool(const float* level, const void* idx, int idx64, int64_t n_q, int64_t n_s, int n_nbrs,
+                                 float* out, void* stream);
+KPREG_API int kpreg_sine_embed(const float* xyz, int64_t n_rows, int n_dim, int d_model, int num_feats, float scale,
+                               const float* dim_t, float* out, void* stream);
+KPREG_API int kpreg_pack_coarse_workspace_bytes(int n_pairs, size_t* bytes);
+KPREG_API int kpreg_pack_coarse(const float* feats, int ld_f, const float* xyz, const int32_t* lens, int n_pairs, int d_model,
+                                int num_feats, float scale, const float* dim_t, int ns_max, int nt_max, float* src_feats,
+                                float* tgt_feats, float* src_pe, float* tgt_pe, unsigned char* src_mask,
+                                unsigned char* tgt_mask, void* workspace, size_t workspace_bytes, void* stream);
+KPREG_API int kpreg_shuffle_gather(const float* pts, const unsigned char* mask, const int64_t* perm, int64_t n_out,
+                                   int64_t n_in, float* out_pts, unsigned char* out_mask, int64_t* rev, int32_t* status,
+                                   void* stream);
+KPREG_API int kpreg_remap_pairs(const int64_t* corr, int64_t n_pairs, const int64_t* rev_src, int64_t n_src,
+                                const int64_t* rev_tgt, int64_t n_tgt, int64_t* out, unsigned char* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,14 +93,70 @@ def test_shard_pairs_round_robin():
     assert sorted(sum(shards, [])) == list(range(10))
 
 
+@pytest.mark.gpu
 def test_compute_overlaps_matches_reference_formula():
     """compute_overlaps (reference finegrained_kpconv.py:545-571) on a hand-made 2-level pyramid."""
     from kpreg_b200.kpconv import PreprocessorGPU, Preprocessor, compute_overlaps
     assert PreprocessorGPU is Preprocessor
-    pools0 = torch.tensor([[0, 1, 5], [2, 5, 5], [3, 4, 0]])           # 5 = pad (level 0 has 5 points)
+    pools0 = torch.tensor([[0, 1, 5], [2, 5, 5], [3, 4, 0]]).cuda()           # 5 = pad (level 0 has 5 points)
     batch = {'src_overlap': [torch.tensor([True, False, True])], 'tgt_overlap': [torch.tensor([False, True])],
-             'kpconv_meta': {'points': [torch.zeros(5, 3), torch.zeros(3, 3)], 'pools': [pools0, torch.zeros(0, 1)],
+             'kpconv_meta': {'points': [torch.zeros(5, 3).cuda(), torch.zeros(3, 3).cuda()], 'pools': [pools0, torch.zeros(0, 1).cuda()],
                              'stack_lengths': [torch.tensor([3, 2]), torch.tensor([2, 1])]}}
     out = compute_overlaps(batch)
-    assert torch.equal(out['pyr_0'], torch.tensor([1., 0., 1., 0., 1.]))
-    assert torch.allclose(out['pyr_1'], torch.tensor([0.5, 1.0, (0. + 1. + 1.) / 3]))
+    assert torch.equal(out['pyr_0'].cpu(), torch.tensor([1., 0., 1., 0., 1.]))
+    assert torch.allclose(out['pyr_1'].cpu(), torch.tensor([0.5, 1.0, (0. + 1. + 1.) / 3]))
+
+
+@pytest.mark.gpu
+def test_compute_overlaps_matches_reference_fixture():
+    """The overlap pyramid of a 3DMatch-shape pair against the REFERENCE's compute_overlaps run on the reference's own
+    pyramid (tests/golden/make_golden_r2.py): our pyramid (CUDA Preprocessor) + kpreg_overlap_pool, 1e-6 (fp32 sums of
+    <= 40 terms in a different order)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from kpreg_b200 import kpconv_config, synthetic
+    from kpreg_b200.kpconv import Preprocessor, compute_overlaps
+    ov = dict(np.load(os.path.join(GOLDEN, "overlaps_r2.npz")))
+    cfg = kpconv_config("3dmatch")
+    src, tgt, _ = synthetic.threedmatch_pair(seed=2, n_raw=9000)
+    for dt in (torch.int64, torch.int32):
+        meta = Preprocessor(cfg, index_dtype=dt)([torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()])
+        batch = {'src_overlap': [torch.from_numpy(ov["src_overlap"]).cuda()], 'tgt_overlap': [torch.from_numpy(ov["tgt_overlap"]).cuda()],
+                 'kpconv_meta': meta}
+        pyr = compute_overlaps(batch)
+        assert sorted(pyr) == ["pyr_0", "pyr_1", "pyr_2", "pyr_3"]
+        for p in range(4):
+            got, want = pyr[f"pyr_{p}"].cpu().numpy(), ov[f"pyr_{p}"]
+            assert got.shape == want.shape and got.dtype == np.float32
+            assert float(np.abs(got - want).max()) < 1e-6, p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["shuffled_truncated", "shuffled_all", "ordered_truncated"])
+def test_shuffle_points_matches_reference(case):
+    """ShufflePoints on the device against the REFERENCE class run with the same numpy seed (exact: gathers and index maps)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from kpreg_b200.ingest import ShufflePoints
+    g = dict(np.load(os.path.join(GOLDEN, "shuffle_points.npz")))
+    max_pts, shuffle = (int(v) for v in g[f"{case}::args"])
+    data = {k.split("::")[-1]: torch.from_numpy(v).cuda() for k, v in g.items() if k.startswith(f"{case}::in::")}
+    np.random.seed(5)
+    out = ShufflePoints(max_pts=max_pts, shuffle=bool(shuffle))(data)
+    for key in ("src_xyz", "tgt_xyz", "src_overlap", "tgt_overlap", "correspondences"):
+        want = g[f"{case}::out::{key}"]
+        got = out[key].cpu().numpy()
+        assert got.shape == want.shape and got.dtype == want.dtype, (key, got.dtype, want.dtype)
+        assert np.array_equal(got, want), key
+
+
+@pytest.mark.gpu
+def test_load_cloud_reads_the_reference_pth_format(tmp_path):
+    import numpy as np
+    from kpreg_b200.ingest import load_cloud
+    cloud = np.random.default_rng(0).normal(size=(1234, 3)).astype(np.float32)
+    torch.save(cloud, tmp_path / "cloud_bin_0.pth")        # the 3DMatch fragments are pickled numpy arrays
+    got = load_cloud(str(tmp_path / "cloud_bin_0.pth"))
+    assert got.is_cuda and got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), cloud)
