@@ -21,6 +21,10 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
+int launch_gemm_tn(const float* a, int lda, const float* b, int ldb, const float* row_scale, float* c, int ldc, int64_t k_rows,
+                   int ma_dim, int nb_dim, int c_transposed, void* split_ws, cudaStream_t stream);
+size_t gemm_tn_workspace_bytes(int64_t k_rows, int nb_dim);
+bool gemm_tn_supported(int64_t k_rows, int ma_dim, int nb_dim, int lda, const void* a);
 
 namespace {
 
@@ -162,13 +166,73 @@ __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__
   }
 }
 
-struct NormWs { int64_t* off; double* stats; float2* mr; size_t total; };
+// Backward of the per-cloud instance norm, y = (x - mean) * rstd:
+//   dx = rstd * (dy - mean_n(dy) - xhat * mean_n(dy * xhat)),  xhat = (x - mean) * rstd, means over the cloud's rows.
+// bstats[(cloud * C + ch) * 2 + {0,1}] += {sum dy, sum dy * xhat} in fp64 — same tiling as k_segnorm_stats.
+__global__ void __launch_bounds__(256) k_segnorm_bstats(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int ld_dy,
+                                                        const int64_t* __restrict__ off, int n_clouds, int64_t n_rows, int channels,
+                                                        const float2* __restrict__ mr, double* __restrict__ bstats) {
+  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int ch = blockIdx.y * kStatCh + cx * 4;
+  if (ch >= channels) return;  // channels is a multiple of 4
+  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
+  const int64_t r1 = min(n_rows, r0 + kStatRows);
+  int c = -1;
+  float2 m[4];
+  double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool one_cloud = cloud_of(off, n_clouds, r0) == cloud_of(off, n_clouds, r1 - 1);
+  for (int64_t r = r0 + ry; r < r1; r += 16) {
+    const int cr = (one_cloud && c >= 0) ? c : cloud_of(off, n_clouds, r);
+    if (cr != c) {
+      if (c >= 0) stat_flush(bstats, c, channels, ch, sum, sq);
+      c = cr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { sum[e] = sq[e] = 0.0; m[e] = mr[(int64_t)c * channels + ch + e]; }
+    }
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+    const float4 g = *reinterpret_cast<const float4*>(dy + r * ld_dy + ch);
+    sum[0] += (double)g.x; sq[0] += (double)g.x * (double)((v.x - m[0].x) * m[0].y);
+    sum[1] += (double)g.y; sq[1] += (double)g.y * (double)((v.y - m[1].x) * m[1].y);
+    sum[2] += (double)g.z; sq[2] += (double)g.z * (double)((v.z - m[2].x) * m[2].y);
+    sum[3] += (double)g.w; sq[3] += (double)g.w * (double)((v.w - m[3].x) * m[3].y);
+  }
+  if (c >= 0) stat_flush(bstats, c, channels, ch, sum, sq);
+}
+
+__global__ void __launch_bounds__(256) k_segnorm_bapply(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int ld_dy,
+                                                        const int64_t* __restrict__ off, int n_clouds, int64_t n_rows, int channels,
+                                                        const float2* __restrict__ mr, const double* __restrict__ bstats,
+                                                        float* __restrict__ dx, int ld_dx) {
+  const int c4 = channels >> 2;
+  const int64_t total = n_rows * (int64_t)c4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int ch = (int)(i - r * c4) * 4;
+    const int c = cloud_of(off, n_clouds, r);
+    const float inv_n = 1.0f / (float)max((int64_t)1, off[c + 1] - off[c]);
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+    const float4 g = *reinterpret_cast<const float4*>(dy + r * ld_dy + ch);
+    const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 m = mr[(int64_t)c * channels + ch + e];
+      const double* b = bstats + ((int64_t)c * channels + ch + e) * 2;
+      const float xhat = (vv[e] - m.x) * m.y;
+      o[e] = m.y * (gg[e] - (float)b[0] * inv_n - xhat * ((float)b[1] * inv_n));
+    }
+    *reinterpret_cast<float4*>(dx + r * ld_dx + ch) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+struct NormWs { int64_t* off; double* stats; float2* mr; double* bstats; size_t total; };
 NormWs carve_norm(void* base, int n_clouds, int channels) {
   NormWs w;
   Carver cv(base);
   w.off = cv.take<int64_t>((size_t)n_clouds + 1);
   w.stats = cv.take<double>((size_t)n_clouds * channels * 2);
   w.mr = cv.take<float2>((size_t)n_clouds * channels);
+  w.bstats = cv.take<double>((size_t)n_clouds * channels * 2);
   w.total = align_up(cv.used, 256);
   return w;
 }
@@ -260,5 +324,75 @@ extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t
   if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
   k_segnorm_apply<<<blocks, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.mr, residual, ld_res, act, slope, out, ldo);
   KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_segment_norm_backward(const float* x, int ldx, const float* dy, int ld_dy, const int32_t* lens, int n_clouds,
+                                           int64_t n_rows, int channels, float eps, float* dx, int ld_dx, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  if (n_rows < 0 || n_clouds < 1 || channels < 4 || (channels & 3) || (ldx & 3) || (ld_dy & 3) || (ld_dx & 3)) return KPREG_E_INVALID;
+  if (n_rows == 0) return KPREG_OK;
+  if (!x || !dy || !lens || !dx || !workspace) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NormWs w = carve_norm(workspace, n_clouds, channels);
+  if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
+  ProfScope prof(KPREG_FAM_NORM, stream);
+  int rc = launch_cloud_offsets(lens, n_clouds, w.off, stream);
+  if (rc) return rc;
+  // the forward statistics are recomputed from x (one extra pass; nothing is kept alive between forward and backward)
+  KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
+  KP_CUDA_TRY(cudaMemsetAsync(w.bstats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
+  dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
+  k_segnorm_stats<<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  KP_LAUNCH_CHECK();
+  k_segnorm_finalize<<<ceil_div((int64_t)n_clouds * channels, 256), 256, 0, stream>>>(w.stats, w.off, n_clouds, channels, eps, w.mr);
+  KP_LAUNCH_CHECK();
+  k_segnorm_bstats<<<grid, 256, 0, stream>>>(x, ldx, dy, ld_dy, w.off, n_clouds, n_rows, channels, w.mr, w.bstats);
+  KP_LAUNCH_CHECK();
+  int blocks = ceil_div(n_rows * (int64_t)(channels >> 2), 256);
+  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  k_segnorm_bapply<<<blocks, 256, 0, stream>>>(x, ldx, dy, ld_dy, w.off, n_clouds, n_rows, channels, w.mr, w.bstats, dx, ld_dx);
+  KP_LAUNCH_CHECK();
+  return KPREG_OK;
+}
+
+// ---- nn.Linear backward on the tensor cores -----------------------------------------------------------------------
+extern "C" int kpreg_linear_backward_workspace_bytes(int64_t m_rows, int k_dim, int n_dim, size_t* bytes) {
+  if (!bytes || m_rows < 0 || k_dim < 1 || n_dim < 1) return KPREG_E_INVALID;
+  *bytes = align_up(kpconv_gemm_tc_weight_bytes(n_dim, k_dim), 256) + gemm_tn_workspace_bytes(m_rows, k_dim < n_dim ? k_dim : n_dim) + 256;
+  return KPREG_OK;
+}
+
+extern "C" int kpreg_linear_backward(const float* x, int ldx, const float* dy, int ld_dy, const float* weight, int64_t m_rows,
+                                     int k_dim, int n_dim, float* dx, int ld_dx, float* d_weight, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+  if (m_rows < 0 || k_dim < 1 || n_dim < 1 || ldx < k_dim || ld_dy < n_dim) return KPREG_E_INVALID;
+  if (!x || !dy || !weight || !workspace || (dx && ld_dx < k_dim)) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (d_weight) KP_CUDA_TRY(cudaMemsetAsync(d_weight, 0, sizeof(float) * (size_t)n_dim * (size_t)k_dim, stream));
+  if (m_rows == 0) return KPREG_OK;
+  size_t need = 0;
+  kpreg_linear_backward_workspace_bytes(m_rows, k_dim, n_dim, &need);
+  if (need > workspace_bytes) return KPREG_E_WORKSPACE;
+  // both products must be addressable by the TMA paths; the caller falls back to its own kernels otherwise
+  if ((dx && !gemm_tc_supported(m_rows, n_dim, k_dim, ld_dy, dy)) ||
+      (d_weight && (!gemm_tn_supported(m_rows, n_dim, k_dim, ld_dy, dy) || !gemm_tn_supported(m_rows, k_dim, n_dim, ldx, x))))
+    return KPREG_E_INVALID;
+  ProfScope prof(KPREG_FAM_LINEAR, stream);
+  float* w_split = static_cast<float*>(workspace);
+  void* tn_split = static_cast<char*>(workspace) + align_up(kpconv_gemm_tc_weight_bytes(n_dim, k_dim), 256);
+  if (dx) {
+    // dx[M, K] = dy[M, N] W[N, K]: the forward kernel with W^T ([k = N, n = K], given as [kd, n] row-major) as its operand
+    int rc = kpconv_gemm_tc_prepare_weights(weight, n_dim, k_dim, 1, w_split, stream);
+    if (rc) return rc;
+    rc = launch_gemm_tc(dy, ld_dy, w_split, dx, ld_dx, m_rows, n_dim, k_dim, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr,
+                        0, nullptr, 0, nullptr, 0, 0, stream);
+    if (rc) return rc;
+  }
+  if (d_weight) {
+    // d_weight[N, K] = dy^T x, reduction over the rows; the narrower operand is the one copied (pre-split) once
+    if (k_dim <= n_dim) return launch_gemm_tn(dy, ld_dy, x, ldx, nullptr, d_weight, k_dim, m_rows, n_dim, k_dim, 0, tn_split, stream);
+    return launch_gemm_tn(x, ldx, dy, ld_dy, nullptr, d_weight, k_dim, m_rows, k_dim, n_dim, 1, tn_split, stream);
+  }
   return KPREG_OK;
 }

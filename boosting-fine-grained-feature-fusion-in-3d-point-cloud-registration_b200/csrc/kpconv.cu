@@ -29,6 +29,11 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
+// kpconv_gemm_tn.cu: tcgen05 split-K weight-gradient GEMM  C += A^T (B * row_scale)
+int launch_gemm_tn(const float* a, int lda, const float* b, int ldb, const float* row_scale, float* c, int ldc, int64_t k_rows,
+                   int ma_dim, int nb_dim, int c_transposed, void* split_ws, cudaStream_t stream);
+size_t gemm_tn_workspace_bytes(int64_t k_rows, int nb_dim);
+bool gemm_tn_supported(int64_t k_rows, int ma_dim, int nb_dim, int lda, const void* a);
 
 namespace {
 
@@ -680,7 +685,7 @@ int launch_gemm(const float* A, const float* B, float* C, const float* row_scale
 }
 
 struct KpconvWs {
-  unsigned char* row_pos; float* inv_num; float* agg; float* d_agg; float* g_scaled; float* w_split; size_t total;
+  unsigned char* row_pos; float* inv_num; float* agg; float* d_agg; float* g_scaled; float* w_split; void* tn_split; size_t total;
 };
 
 KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in, int c_out, int backward) {
@@ -692,11 +697,16 @@ KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in
   w.agg = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * kd);
   w.d_agg = nullptr;
   w.g_scaled = nullptr;
+  w.tn_split = nullptr;
+  size_t w_bytes = kpconv_gemm_tc_weight_bytes((int)kd, c_out);
   if (backward) {
     w.d_agg = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * kd);
     w.g_scaled = cv.take<float>((size_t)(n_q > 0 ? n_q : 1) * (size_t)c_out);
+    w.tn_split = cv.take<char>(gemm_tn_workspace_bytes(n_q, c_out));
+    const size_t wt_bytes = kpconv_gemm_tc_weight_bytes(c_out, (int)kd);  // the weights as the operand of d_agg = g' W^T
+    if (wt_bytes > w_bytes) w_bytes = wt_bytes;
   }
-  w.w_split = reinterpret_cast<float*>(cv.take<char>(kpconv_gemm_tc_weight_bytes((int)kd, c_out)));
+  w.w_split = reinterpret_cast<float*>(cv.take<char>(w_bytes));
   w.total = align_up(cv.used, 256);
   return w;
 }
@@ -912,6 +922,24 @@ extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, con
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
     k_scale_rows<<<blocks, 256, 0, stream>>>(grad_out, w.inv_num, n_q, c_out, w.g_scaled);
     KP_LAUNCH_CHECK();
+  }
+  static const bool bwd_fp32 = [] { const char* e = getenv("KPREG_BACKWARD_FP32"); return e && e[0] == '1'; }();  // A/B measurements
+  if (!bwd_fp32 && gemm_tn_supported(n_q, kd, c_out, kd, w.agg) && gemm_tc_supported(n_q, c_out, kd, c_out, w.g_scaled)) {
+    // both contractions of the backward pass on tcgen05 (3xTF32):
+    //   d_weights[K*c_in, c_out] += agg^T (grad_out / num)     split over the queries, operands taken MN-major as they lie
+    //   d_agg[n_q, K*c_in]        = (grad_out / num) W^T       the forward kernel with W^T as its K-major operand
+    ProfScope prof(KPREG_FAM_CONTRACT, stream);
+    rc = launch_gemm_tn(w.agg, kd, grad_out, c_out, w.inv_num, d_weights, c_out, n_q, kd, c_out, 0, w.tn_split, stream);
+    if (rc) return rc;
+    rc = kpconv_gemm_tc_prepare_weights(weights, c_out, kd, 0, w.w_split, stream);  // W as [n = K*c_in, k = c_out]
+    if (rc) return rc;
+    rc = launch_gemm_tc(w.g_scaled, c_out, w.w_split, w.d_agg, kd, n_q, c_out, kd, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f,
+                        nullptr, 0, nullptr, 0, nullptr, 0, 0, stream);
+    if (rc) return rc;
+    return idx64 ? launch_scatter<int64_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                           influence, aggregation, d_x, order, stream)
+                 : launch_scatter<int32_t>(q_pts, s_pts, idx, kernel_points, w.d_agg, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+                                           influence, aggregation, d_x, order, stream);
   }
   // d_weights[K*c_in, c_out] = agg^T g'   (reduction over the queries, split across CTAs)
   {

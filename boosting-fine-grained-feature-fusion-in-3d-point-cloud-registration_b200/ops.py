@@ -419,6 +419,60 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
 
 
 @_on_tensor_device
+def linear_backward(x, grad_out, weight, need_dx: bool = True, need_dw: bool = True):
+    """(dx [M,K] or None, d_weight [N,K] or None) of y = x weight^T on the tensor cores (kpreg_linear_backward).
+    Returns None when a shape is outside the TMA paths: the caller then uses torch."""
+    lib = _lib.load()
+    x, ldx = _rows(x, "x")
+    grad_out, ldg = _rows(grad_out, "grad_out")
+    weight = _f32c(weight, "weight")
+    m, k = x.shape
+    n = weight.shape[0]
+    if (m == 0 or k < 8 or n < 8 or ldx % 4 or ldg % 4 or x.data_ptr() % 16 or grad_out.data_ptr() % 16 or k % 4 or n % 4):
+        return None
+    dev = x.device
+    dx = torch.empty((m, k), dtype=torch.float32, device=dev) if need_dx else None
+    dw = torch.empty((n, k), dtype=torch.float32, device=dev) if need_dw else None
+    nbytes = _lib.size_query("kpreg_linear_backward_workspace_bytes", m, k, n)
+    ws = _lib.workspaces.get(nbytes, dev)
+    rc = lib.kpreg_linear_backward(x.data_ptr(), ldx, grad_out.data_ptr(), ldg, weight.data_ptr(), m, k, n, _lib.ptr(dx), k,
+                                   _lib.ptr(dw), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    if rc == 1:
+        return None
+    _lib.check(rc, "kpreg_linear_backward")
+    return dx, dw
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x weight^T (no bias) with forward, dx and d_weight on the tcgen05 3xTF32 GEMMs — the training-mode stand-in
+    for the nn.Linear layers of the encoder blocks (fp32-grade results, unlike TF32-allowed cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return linear_forward(x, weight, gemm=1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad
+        res = linear_backward(x, grad, weight, need_dx, need_dw)
+        if res is None:
+            g = grad.to(torch.float32)
+            return (g @ weight if need_dx else None), (g.t() @ x if need_dw else None)
+        return res
+
+
+def linear_train(x: torch.Tensor, linear: torch.nn.Linear) -> torch.Tensor:
+    """``linear(x)`` for a bias-free nn.Linear under autograd: tensor-core kernels when the shape allows, torch otherwise."""
+    if (torch.is_grad_enabled() and (x.requires_grad or linear.weight.requires_grad)
+            and linear.bias is None and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] > 0
+            and x.shape[1] % 4 == 0 and x.shape[1] >= 8 and linear.out_features % 4 == 0 and linear.out_features >= 8):
+        return LinearFn.apply(x, linear.weight)
+    return linear(x)
+
+
+@_on_tensor_device
 def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: float = 1e-5, out=None):
     """Per-cloud, per-channel (x - mean) * rstd (+ residual) (+ activation) (kpreg_segment_norm_forward)."""
     lib = _lib.load()
@@ -439,6 +493,23 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
                                         ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_segment_norm_forward")
     return out
+
+
+@_on_tensor_device
+def segment_norm_backward(x, grad_out, lens, eps: float = 1e-5):
+    """d/dx of the plain per-cloud norm (kpreg_segment_norm_backward)."""
+    lib = _lib.load()
+    x, ldx = _rows(x, "x")
+    grad_out, ldg = _rows(grad_out, "grad_out")
+    lens = _i32c(lens, "stack_lengths")
+    n, c = x.shape
+    dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    nbytes = _lib.size_query("kpreg_segment_norm_workspace_bytes", int(lens.shape[0]), c)
+    ws = _lib.workspaces.get(nbytes, x.device)
+    rc = lib.kpreg_segment_norm_backward(x.data_ptr(), ldx, grad_out.data_ptr(), ldg, lens.data_ptr(), int(lens.shape[0]), n, c,
+                                         float(eps), dx.data_ptr(), c, ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device))
+    _lib.check(rc, "kpreg_segment_norm_backward")
+    return dx
 
 
 class ChainPack:

@@ -135,16 +135,18 @@ class my_Bottle2neck(_CacheInvalidating):
             from . import kpconv_blocks as kb
             if kb.FUSED_GLUE:
                 return self._fused_forward(x, shortcut)
-        groups = torch.split(self.relu(self.bn1(self.conv1(x))), self.width, 1)
+        from . import ops
+        lin = ops.linear_train  # bias-free nn.Linear under autograd: tensor-core forward / dx / d_weight where the shape allows
+        groups = torch.split(self.relu(self.bn1(lin(x, self.conv1))), self.width, 1)
         outs, carry = [], None
         for i in range(self.nums):
             carry = groups[i] if (i == 0 or self.stype == 'stage') else carry + groups[i]
-            carry = self.relu(self.bns[i](self.convs[i](carry)))
+            carry = self.relu(self.bns[i](lin(carry.contiguous(), self.convs[i])))
             outs.append(carry)
         if self.scale != 1:
             outs.append(groups[self.nums] if self.stype == 'normal' else self.pool(groups[self.nums]))
-        out = self.bn3(self.conv3(torch.cat(outs, 1)))
-        residual = x if self.downsample is None else self.downsample(x)
+        out = self.bn3(lin(torch.cat(outs, 1), self.conv3))
+        residual = x if self.downsample is None else self.downsample[1](lin(x, self.downsample[0]))
         out = self.relu(out + residual)
         return out if shortcut is None else torch.nn.functional.leaky_relu(out + shortcut, 0.1)
 

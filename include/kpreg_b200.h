@@ -198,10 +198,22 @@ KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight,
                                    int act, float slope, float* out, int ldc, float* out2, int ld2, const float* addend,
                                    int ld_add, const float* post_residual, int ld_post, int post_act, int gemm,
                                    void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of y = x W^T on the tensor cores (3xTF32): dx [M, K] = dy W (may be NULL) and d_weight [N, K] = dy^T x (may be
+ * NULL; a split-k reduction over the M rows, accumulated with fp32 atomics).  Returns KPREG_E_INVALID when a shape is not
+ * addressable by the TMA paths (K or N < 8, pitches / bases not 16-byte aligned): the caller then uses its own kernels. */
+KPREG_API int kpreg_linear_backward_workspace_bytes(int64_t m_rows, int k_dim, int n_dim, size_t* bytes);
+KPREG_API int kpreg_linear_backward(const float* x, int ldx, const float* dy, int ld_dy, const float* weight, int64_t m_rows,
+                                    int k_dim, int n_dim, float* dx, int ld_dx, float* d_weight, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 KPREG_API int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes);
 KPREG_API int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
                                          int channels, float eps, const float* residual, int ld_res, int act, float slope,
                                          float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the plain norm (no residual / activation): dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) per cloud and
+ * channel, statistics recomputed from x.  Same workspace size as the forward. */
+KPREG_API int kpreg_segment_norm_backward(const float* x, int ldx, const float* dy, int ld_dy, const int32_t* lens,
+                                          int n_clouds, int64_t n_rows, int channels, float eps, float* dx, int ld_dx,
+                                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The hierarchical chain of my_Bottle2neck in one kernel (models/backbone_kpconv/res2net.py:137-150):

@@ -184,3 +184,39 @@ def test_res2net_unit_with_fused_shortcut():
             kpconv_blocks.FUSED_GLUE = True
     assert rel_err(fused.cpu().numpy(), stock.cpu().numpy()) < 1e-5
     assert torch.equal(stock, stock2)
+
+
+@pytest.mark.parametrize("m,k,n", [(5000, 32, 128), (20000, 128, 32), (3001, 256, 224), (777, 64, 64), (12345, 1024, 256), (40, 16, 8)])
+def test_linear_autograd_on_tensor_cores(m, k, n):
+    """y = x W^T, dx = dy W and dW = dy^T x (split-k over the rows, MN-major tcgen05 operands) against fp64."""
+    torch.manual_seed(m)
+    x = torch.randn(m, k, device="cuda", requires_grad=True)
+    lin = torch.nn.Linear(k, n, bias=False).cuda()
+    g = torch.randn(m, n, device="cuda")
+    y = ops.linear_train(x, lin)
+    assert y.grad_fn is not None and "LinearFn" in type(y.grad_fn).__name__
+    y.backward(g)
+    x64, w64, g64 = x.detach().double(), lin.weight.detach().double(), g.double()
+    assert rel_err(y.detach().cpu().numpy(), (x64 @ w64.t()).cpu().numpy()) < 1e-5
+    assert rel_err(x.grad.cpu().numpy(), (g64 @ w64).cpu().numpy()) < 1e-5
+    assert rel_err(lin.weight.grad.cpu().numpy(), (g64.t() @ x64).cpu().numpy()) < 1e-5
+
+
+def test_segment_norm_backward_matches_torch_autograd():
+    from kpreg_b200.kpconv_blocks import _SegNormFn, _segment_instance_norm
+    torch.manual_seed(0)
+    lens = torch.tensor([700, 1, 1300, 2999, 256, 3], dtype=torch.int32, device="cuda")
+    n = int(lens.sum())
+    for c in (32, 128, 68):
+        x = (torch.randn(n, c, device="cuda") * 3 + 1).requires_grad_(True)
+        g = torch.randn(n, c, device="cuda")
+        y = _SegNormFn.apply(x, lens)
+        y.backward(g)
+        x64 = x.detach().double().requires_grad_(True)
+        y64 = _segment_instance_norm(x64, lens)
+        y64.backward(g.double())
+        assert rel_err(y.detach().cpu().numpy(), y64.detach().cpu().numpy()) < 1e-5
+        # single-point clouds have zero variance: rstd = 1/sqrt(eps) amplifies rounding there; compare the rest tightly
+        keep = torch.ones(n, dtype=torch.bool)
+        keep[700] = False
+        assert rel_err(x.grad.cpu()[keep].numpy(), x64.grad.cpu()[keep].numpy()) < 1e-4
