@@ -55,6 +55,26 @@ __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ 
   if (lane == 0) pos[row] = (float)acc > 0.0f ? 1 : 0;
 }
 
+// The same predicate for 16-byte aligned rows of c_in = 4 * k channels: G = 2^m >= c_in / 4 lanes per row read one float4 each
+// (32 / G rows per warp and load instruction), so short rows — 128 bytes at c_in = 32 — still move 512 bytes per instruction.
+template <int G>
+__global__ void __launch_bounds__(256) k_row_positive_vec(const float* __restrict__ x, int64_t n_s, int c_in,
+                                                          unsigned char* __restrict__ pos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t / G;
+  const int sub = (int)(t - row * G);
+  double acc = 0.0;
+  if (row < n_s) {
+    for (int c = 4 * sub; c < c_in; c += 4 * G) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * c_in + c));
+      acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < n_s && sub == 0) pos[row] = (float)acc > 0.0f ? 1 : 0;
+}
+
 // rsqrt.approx.ftz: the argument is clamped to >= 1e-30 (a normal number) by every caller, so the denormal pre-scaling
 // that rsqrtf() compiles to (a compare and two conditional multiplies per call) can never trigger.
 __device__ __forceinline__ float rsqrt_fast(float x) {
@@ -338,6 +358,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
       step_influences(h0, va, vb, a_hi, a_lo);
       const float* __restrict__ xa = x + (int64_t)(va ? ja : 0) * c_in;
       const float* __restrict__ xb = x + (int64_t)(vb ? jb : 0) * c_in;
+      // (Measured: feeding the B operand pre-split — features split once per layer into interleaved (hi, lo) pairs instead of
+      // once per gathering lane, 30 % fewer instructions — made the step's aggregate kernels 40 % SLOWER: the kernel is bound
+      // by the gather path (L1 / L2 latency at a 78 % L1 hit rate), and pre-split rows are twice as long.)
       if constexpr (VEC) {
         float4 fa[NT / 4], fb[NT / 4];
 #pragma unroll
@@ -399,9 +422,6 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
   }
 }
 
-#ifdef KPREG_EXPERIMENTAL_GATHER_ASYNC
-#include "kpconv_gather_async.cuh"  // cp.async ring variant of the aggregate kernel: not validated on hardware, off by default
-#endif
 
 // ---- c_in == 1 (the encoder's first block: a single input feature per point) ----------------------------
 // With one channel the aggregate is 15 numbers per query and the contraction a [15] x [15, c_out] product, so the whole
@@ -711,6 +731,21 @@ KpconvWs carve_kpconv(void* base, int64_t n_q, int64_t n_s, int n_kpts, int c_in
   return w;
 }
 
+// The normalisation's row predicate (feature sum > 0) of the support rows: part of the aggregate step
+void launch_row_pass(const float* x, int64_t n_s, int c_in, unsigned char* row_pos, cudaStream_t stream) {
+  if (n_s == 0) return;
+  if ((c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int q = c_in / 4;
+    if (q <= 4) k_row_positive_vec<4><<<ceil_div(n_s * 4, 256), 256, 0, stream>>>(x, n_s, c_in, row_pos);
+    else if (q <= 8) k_row_positive_vec<8><<<ceil_div(n_s * 8, 256), 256, 0, stream>>>(x, n_s, c_in, row_pos);
+    else if (q <= 16) k_row_positive_vec<16><<<ceil_div(n_s * 16, 256), 256, 0, stream>>>(x, n_s, c_in, row_pos);
+    else k_row_positive_vec<32><<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, row_pos);
+  } else {
+    k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, row_pos);
+  }
+  count_launches(1);
+}
+
 template <typename IdxT>
 int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const float* x, const unsigned char* row_pos,
                   const float* kp, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence,
@@ -731,27 +766,6 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   } while (0)
     // float4 path: whole rows of x and of the aggregate are 16-byte aligned
     const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
-#ifdef KPREG_EXPERIMENTAL_GATHER_ASYNC
-    static const bool use_async = [] { const char* e = getenv("KPREG_GATHER_ASYNC"); return e && e[0] == '1'; }();
-    if (use_async && vec && c_in > 16 && c_in <= 128) {
-#define KP_GATHER_ASYNC(NT)                                                                                                     \
-  do {                                                                                                                          \
-    const size_t smem = (size_t)kGatherWarps * kRingStages * 16 * NT * sizeof(float4);                                          \
-    if (influence == 1)                                                                                                         \
-      k_kpconv_gather_async<IdxT, NT, 1><<<blocks, kGatherWarps * 32, smem, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, \
-                                                                                      n_nbrs, n_kpts, c_in, extent, influence,   \
-                                                                                      aggregation, agg, inv_num, order);          \
-    else                                                                                                                        \
-      k_kpconv_gather_async<IdxT, NT, -1><<<blocks, kGatherWarps * 32, smem, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, \
-                                                                                       n_nbrs, n_kpts, c_in, extent, influence,  \
-                                                                                       aggregation, agg, inv_num, order);         \
-  } while (0)
-      if (c_in <= 32) KP_GATHER_ASYNC(4); else if (c_in <= 64) KP_GATHER_ASYNC(8); else KP_GATHER_ASYNC(16);
-#undef KP_GATHER_ASYNC
-      KP_LAUNCH_CHECK();
-      return KPREG_OK;
-    }
-#endif
     if (c_in <= 8) KP_GATHER_MMA(1, false);
     else if (c_in <= 16) KP_GATHER_MMA(2, false);
     else if (c_in <= 32) { if (vec) KP_GATHER_MMA(4, true); else KP_GATHER_MMA(4, false); }
@@ -863,9 +877,10 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   }
   KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 0);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
-  if (n_s > 0) {
-    k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, w.row_pos);
-    KP_LAUNCH_CHECK();
+  {
+    ProfScope prof_rows(KPREG_FAM_GATHER, stream);  // the row pass belongs to the aggregate step
+    launch_row_pass(x, n_s, c_in, w.row_pos, stream);
+    KP_CUDA_TRY(cudaPeekAtLastError());
   }
   rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
                                       influence, aggregation, w.agg, w.inv_num, order, stream)
@@ -909,8 +924,8 @@ extern "C" int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, con
   KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 1);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
   // recompute the aggregate and the normalisation (cheaper than keeping [n_q, K*c_in] alive per layer)
-  k_row_positive<<<ceil_div(n_s * 32, 256), 256, 0, stream>>>(x, n_s, c_in, w.row_pos);
-  KP_LAUNCH_CHECK();
+  launch_row_pass(x, n_s, c_in, w.row_pos, stream);
+  KP_CUDA_TRY(cudaPeekAtLastError());
   rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
                                       influence, aggregation, w.agg, w.inv_num, order, stream)
              : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,

@@ -8,7 +8,8 @@
 namespace kpreg {
 namespace {
 
-template <typename IdxT>
+// ARGMAX = false (inference): the winning row is not tracked — a third fewer instructions in the inner loop
+template <typename IdxT, bool ARGMAX>
 __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, const IdxT* __restrict__ idx, int64_t n_q, int64_t n_s,
                                                   int n_nbrs, int channels, float* __restrict__ out, int32_t* __restrict__ argmax,
                                                   const int32_t* __restrict__ order) {
@@ -37,10 +38,15 @@ __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, c
           else v.x = x[jj * channels + c];
         }
         // strict > keeps the first maximum, like a sequential scan over the row
-        if (v.x > best[0]) { best[0] = v.x; best_j[0] = (int32_t)jj; }
-        if (v.y > best[1]) { best[1] = v.y; best_j[1] = (int32_t)jj; }
-        if (v.z > best[2]) { best[2] = v.z; best_j[2] = (int32_t)jj; }
-        if (v.w > best[3]) { best[3] = v.w; best_j[3] = (int32_t)jj; }
+        if constexpr (ARGMAX) {
+          if (v.x > best[0]) { best[0] = v.x; best_j[0] = (int32_t)jj; }
+          if (v.y > best[1]) { best[1] = v.y; best_j[1] = (int32_t)jj; }
+          if (v.z > best[2]) { best[2] = v.z; best_j[2] = (int32_t)jj; }
+          if (v.w > best[3]) { best[3] = v.w; best_j[3] = (int32_t)jj; }
+        } else {
+          best[0] = fmaxf(best[0], v.x); best[1] = fmaxf(best[1], v.y);
+          best[2] = fmaxf(best[2], v.z); best[3] = fmaxf(best[3], v.w);
+        }
       }
     }
     if (c < channels) {
@@ -78,8 +84,13 @@ extern "C" int kpreg_max_pool_forward(const float* x, const void* idx, int idx64
   cudaStream_t stream = (cudaStream_t)stream_;
   const int blocks = ceil_div(n_q * 32, 256);
   ProfScope prof(KPREG_FAM_POOL, stream);
-  if (idx64) k_max_pool<int64_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
-  else k_max_pool<int32_t><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+  if (argmax) {
+    if (idx64) k_max_pool<int64_t, true><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+    else k_max_pool<int32_t, true><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+  } else {
+    if (idx64) k_max_pool<int64_t, false><<<blocks, 256, 0, stream>>>(x, static_cast<const int64_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+    else k_max_pool<int32_t, false><<<blocks, 256, 0, stream>>>(x, static_cast<const int32_t*>(idx), n_q, n_s, n_nbrs, channels, out, argmax, order);
+  }
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
