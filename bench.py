@@ -398,10 +398,14 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_out = sys.stdout
     if world > 1:
-        # rank 0 prints exactly one JSON line on stdout: NCCL's own log lines (banner, NCCL_DEBUG=INFO topology / rank lines)
-        # go to stderr instead of being silenced, so that they can still be read
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # rank 0 prints exactly one JSON line on stdout.  NCCL writes its own log lines (version banner, NCCL_DEBUG=INFO
+        # topology / rank lines) to file descriptor 1 from C: point fd 1 at stderr for the life of the process — nothing is
+        # silenced, the lines can still be read there — and keep the original stdout for the JSON line alone.
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     if args.gemm is not None:
         kpconv_blocks.DEFAULT_GEMM = args.gemm
@@ -467,6 +471,8 @@ def main():
             rows.append(result_rows(out))
         return finish(rows, out)
 
+    host_table = [None]
+
     def step_e2e():
         rows, out = [], None
         for b in batches:
@@ -474,7 +480,12 @@ def main():
             out = path(parts[:b.n], parts[b.n:], b.poses_host.to(dev, non_blocking=True), corr=b.corr)
             rows.append(result_rows(out))
         table, out = finish(rows, out)
-        return table.cpu(), out  # D2H of every pair's pose + errors
+        # D2H of every pair's pose + errors into pinned host memory, stream-ordered (inside the step's CUDA events); the host
+        # does not block on it, so a step's launches are not serialised behind the previous step's read-back
+        if host_table[0] is None or host_table[0].shape != table.shape:
+            host_table[0] = torch.empty(table.shape, dtype=table.dtype).pin_memory()
+        host_table[0].copy_(table, non_blocking=True)
+        return host_table[0], out
 
     def timed(fn, steps, warmup, profile):
         if profile:
@@ -643,7 +654,7 @@ def main():
             "final_layer_pose_error": {"rot_deg_max": float(table[:, 12].max()), "trans_max": float(table[:, 13].max()),
                                        "note": "against the generating pose through 1 cm synthetic correspondence noise — not a parity figure"},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
