@@ -9,7 +9,9 @@
 //   t = cb - R ca                                                 (:171)
 // One CTA per set: a block-wide fp64 reduction of the 16 moments
 //   {sum w, sum w a, sum w b, sum w a b^T}  (cov follows from them in closed form),
-// then one warp solves the 3x3 SVD with one-sided Jacobi rotations in fp64.  The reference works
+// then the CTA's first warp solves the 3x3 SVD with one-sided Jacobi rotations in fp64: lane i owns row i of A and of V,
+// the column inner products of a rotation are three-lane shuffle sums, every lane derives the same (c, s) and rotates
+// its own row.  The reference works
 // in fp32 with LAPACK; parity is on the assembled [R|t] (singular vectors are sign/order
 // ambiguous), within 1e-3 deg and 1e-5 m.
 #include "common.cuh"
@@ -30,28 +32,39 @@ __device__ void svd3_rotation(const double cov[3][3], double R[3][3]) {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] = (i == j) ? 1.0 : 0.0;
     return;
   }
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
-    for (int p = 0; p < 2; ++p) {
-      for (int q = p + 1; q < 3; ++q) {
-        double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int i = 0; i < 3; ++i) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
-        if (gamma == 0.0) continue;
-        off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int i = 0; i < 3; ++i) {
-          const double ap = A[i][p], aq = A[i][q];
-          A[i][p] = c * ap - s * aq;
-          A[i][q] = s * ap + c * aq;
-          const double vp = V[i][p], vq = V[i][q];
-          V[i][p] = c * vp - s * vq;
-          V[i][q] = s * vp + c * vq;
+  // Jacobi sweeps across the warp: lane r (< 3) owns row r of A and of V; all 32 lanes execute the shuffles
+  {
+    const int lane = threadIdx.x & 31;
+    const int r = lane < 3 ? lane : 0;
+    double ar[3] = {A[r][0], A[r][1], A[r][2]}, vr[3] = {V[r][0], V[r][1], V[r][2]};
+    const double live = lane < 3 ? 1.0 : 0.0;
+    auto sum3 = [](double v) {  // lanes 0..2 -> every lane
+      return __shfl_sync(0xffffffffu, v, 0) + __shfl_sync(0xffffffffu, v, 1) + __shfl_sync(0xffffffffu, v, 2);
+    };
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      double off = 0.0;
+      for (int p = 0; p < 2; ++p) {
+        for (int q = p + 1; q < 3; ++q) {
+          const double alpha = sum3(live * ar[p] * ar[p]), beta = sum3(live * ar[q] * ar[q]), gamma = sum3(live * ar[p] * ar[q]);
+          if (gamma == 0.0) continue;  // warp-uniform
+          off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+          const double ap = ar[p], aq = ar[q], vp = vr[p], vq = vr[q];
+          ar[p] = c * ap - sn * aq;
+          ar[q] = sn * ap + c * aq;
+          vr[p] = c * vp - sn * vq;
+          vr[q] = sn * vp + c * vq;
         }
       }
+      if (off < 1e-15) break;  // warp-uniform
     }
-    if (off < 1e-15) break;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        A[i][j] = __shfl_sync(0xffffffffu, ar[j], i);
+        V[i][j] = __shfl_sync(0xffffffffu, vr[j], i);
+      }
   }
   // singular values = column norms; order them descending (the reference flips the LAST column)
   double sig[3];
@@ -135,7 +148,7 @@ __global__ void __launch_bounds__(kKabschThreads) k_kabsch(const float* __restri
     if (lane == 0) s_part[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (warp != 0) return;  // the first warp finishes: totals (every lane), warp-level Jacobi SVD, lane 0 writes [R | t]
   double t[16];
   for (int i = 0; i < 16; ++i) {
     t[i] = 0.0;
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(kKabschThreads) k_kabsch(const float* __restri
     for (int j = 0; j < 3; ++j) cov[i][j] = t[7 + 3 * i + j] * inv - ca[i] * cb[j] * (2.0 - sw);
   double R[3][3];
   svd3_rotation(cov, R);
+  if (lane != 0) return;
   float* o = out + set * 12;
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) o[4 * i + j] = (float)R[i][j];
