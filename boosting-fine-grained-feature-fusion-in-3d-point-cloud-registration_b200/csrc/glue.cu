@@ -72,11 +72,14 @@ __device__ __forceinline__ void stat_flush(double* __restrict__ stats, int cloud
 
 // stats[(cloud * C + ch) * 2 + {0,1}] += {sum x, sum x^2} in fp64.  Each thread streams float4 (4 channels) of 16
 // rows; a CTA covers 256 rows x 64 channels and issues one atomic pair per channel when it lies inside one cloud.
+// TX = threads per row (8 for rows of <= 32 channels: no idle lanes), 256 / TX row groups.
+template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
                                                        int n_clouds, int64_t n_rows, int channels, double* __restrict__ stats) {
-  __shared__ double s_sum[16][kStatCh], s_sq[16][kStatCh];
-  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
-  const int ch = blockIdx.y * kStatCh + cx * 4;
+  constexpr int RY = 256 / TX, CH = 4 * TX;
+  __shared__ double s_sum[RY][CH], s_sq[RY][CH];
+  const int cx = threadIdx.x % TX, ry = threadIdx.x / TX;
+  const int ch = blockIdx.y * CH + cx * 4;
   const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
   const int64_t r1 = min(n_rows, r0 + kStatRows);
   const int c_first = cloud_of(off, n_clouds, r0);
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__
   if (c_first == c_last) {
     if (live) {
 #pragma unroll 4
-      for (int64_t r = r0 + ry; r < r1; r += 16) {
+      for (int64_t r = r0 + ry; r < r1; r += RY) {
         const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
         sum[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
         sum[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
@@ -97,12 +100,12 @@ __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__
 #pragma unroll
     for (int e = 0; e < 4; ++e) { s_sum[ry][cx * 4 + e] = sum[e]; s_sq[ry][cx * 4 + e] = sq[e]; }
     __syncthreads();
-    if (threadIdx.x < kStatCh) {
-      const int c = blockIdx.y * kStatCh + threadIdx.x;
+    if (threadIdx.x < CH) {
+      const int c = blockIdx.y * CH + threadIdx.x;
       if (c < channels) {
         double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) { a += s_sum[g][threadIdx.x]; b += s_sq[g][threadIdx.x]; }
+        for (int g = 0; g < RY; ++g) { a += s_sum[g][threadIdx.x]; b += s_sq[g][threadIdx.x]; }
         double* dst = stats + ((int64_t)c_first * channels + c) * 2;
         atomicAdd(dst, a);
         atomicAdd(dst + 1, b);
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__
   } else if (live) {
     // chunk straddles a cloud boundary: flush per thread whenever the cloud changes
     int c = -1;
-    for (int64_t r = r0 + ry; r < r1; r += 16) {
+    for (int64_t r = r0 + ry; r < r1; r += RY) {
       const int cr = cloud_of(off, n_clouds, r);
       if (cr != c) {
         if (c >= 0) stat_flush(stats, c, channels, ch, sum, sq);
@@ -142,20 +145,42 @@ __global__ void __launch_bounds__(256) k_segnorm_finalize(const double* __restri
   mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
+// y = act((x - mean) * rstd + residual).  Same tiling as k_segnorm_stats (a CTA = 256 rows x 64 channels, a thread = 4
+// channels of every 16th row), so a thread's channels are fixed and its cloud changes at most a few times: mean / rstd are
+// derived from the fp64 moments in registers when the cloud changes (no separate finalize launch, no per-element
+// cloud search, no per-element statistics loads) — biased variance, eps inside the sqrt.  TX = threads per row
+// (4 TX channels per CTA column): 8 for narrow rows so that no lane idles at 32 channels.
+template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
-                                                       int n_clouds, int64_t n_rows, int channels, const float2* __restrict__ mr,
-                                                       const float* __restrict__ residual, int ld_res, int act, float slope,
+                                                       int n_clouds, int64_t n_rows, int channels, const double* __restrict__ stats,
+                                                       float eps, const float* __restrict__ residual, int ld_res, int act, float slope,
                                                        float* __restrict__ out, int ldo) {
-  const int c4 = channels >> 2;
-  const int64_t total = n_rows * (int64_t)c4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / c4;
-    const int ch = (int)(i - r * c4) * 4;
-    const int c = cloud_of(off, n_clouds, r);
+  constexpr int RY = 256 / TX;
+  const int cx = threadIdx.x % TX, ry = threadIdx.x / TX;
+  const int ch = blockIdx.y * (4 * TX) + cx * 4;
+  if (ch >= channels) return;  // channels is a multiple of 4
+  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
+  const int64_t r1 = min(n_rows, r0 + kStatRows);
+  int c = -1;
+  int64_t c_end = 0;
+  float mean[4], rstd[4];
+  for (int64_t r = r0 + ry; r < r1; r += RY) {
+    if (c < 0 || r >= c_end) {
+      c = cloud_of(off, n_clouds, r);
+      c_end = off[c + 1];
+      const double n = (double)max((int64_t)1, c_end - off[c]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double* st = stats + ((int64_t)c * channels + ch + e) * 2;
+        const double m = st[0] / n;
+        double var = st[1] / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[e] = (float)m;
+        rstd[e] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
     const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
-    const float2* m = mr + (int64_t)c * channels + ch;
-    const float2 m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
-    float4 y = make_float4((v.x - m0.x) * m0.y, (v.y - m1.x) * m1.y, (v.z - m2.x) * m2.y, (v.w - m3.x) * m3.y);
+    float4 y = make_float4((v.x - mean[0]) * rstd[0], (v.y - mean[1]) * rstd[1], (v.z - mean[2]) * rstd[2], (v.w - mean[3]) * rstd[3]);
     if (residual) {
       const float4 q = *reinterpret_cast<const float4*>(residual + r * ld_res + ch);
       y.x += q.x; y.y += q.y; y.z += q.z; y.w += q.w;
@@ -316,13 +341,19 @@ extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t
   if (rc) return rc;
   KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
   dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
-  k_segnorm_stats<<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  if (channels <= 32) {
+    dim3 grid_s((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
+    k_segnorm_stats<8><<<grid_s, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  } else {
+    k_segnorm_stats<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  }
   KP_LAUNCH_CHECK();
-  k_segnorm_finalize<<<ceil_div((int64_t)n_clouds * channels, 256), 256, 0, stream>>>(w.stats, w.off, n_clouds, channels, eps, w.mr);
-  KP_LAUNCH_CHECK();
-  int blocks = ceil_div(n_rows * (int64_t)(channels >> 2), 256);
-  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
-  k_segnorm_apply<<<blocks, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.mr, residual, ld_res, act, slope, out, ldo);
+  if (channels <= 32) {
+    dim3 grid_a((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
+    k_segnorm_apply<8><<<grid_a, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo);
+  } else {
+    k_segnorm_apply<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo);
+  }
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -343,7 +374,12 @@ extern "C" int kpreg_segment_norm_backward(const float* x, int ldx, const float*
   KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
   KP_CUDA_TRY(cudaMemsetAsync(w.bstats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
   dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
-  k_segnorm_stats<<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  if (channels <= 32) {
+    dim3 grid_s((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
+    k_segnorm_stats<8><<<grid_s, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  } else {
+    k_segnorm_stats<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
+  }
   KP_LAUNCH_CHECK();
   k_segnorm_finalize<<<ceil_div((int64_t)n_clouds * channels, 256), 256, 0, stream>>>(w.stats, w.off, n_clouds, channels, eps, w.mr);
   KP_LAUNCH_CHECK();
