@@ -37,6 +37,7 @@
 //     every role ran it per tile);
 //   * a staged tile flushed by coalesced STG.128 instead of the TMA store was 20-40 % slower.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,35 @@ constexpr int gemm_threads(int block_n) { return 64 + 128 + 32 * (block_n >= 64 
 constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 
 using namespace tc;  // PTX wrappers (tc_ptx.cuh)
+
+// ---- fp16 operand split (H2 variant) ---------------------------------------------------------------------------
+// x = hi + lo' * 2^-11 with hi = fp16(x) (11 significant bits, like TF32) and lo' = fp16((x - hi) * 2^11): 22 bits in all —
+// the same budget as the 3xTF32 split — but `kind::f16` runs at twice the TF32 rate, an operand element is 2 bytes instead
+// of 4 (the mainloop is bound by shared-memory bandwidth) and K is 16 per instruction.  The cross terms are accumulated
+// unscaled in their own TMEM accumulator and scaled by 2^-11 in the epilogue.  Range: |x| < 65504 (fp16); magnitudes
+// below 6e-5 keep an absolute accuracy of 6e-8.  KPREG_GEMM_TF32=1 selects the TF32 kernel instead.
+constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
+}
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 32 halves): 8-row groups 512 B apart, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, shape M x N x 16.
+__device__ __forceinline__ uint32_t make_instr_desc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 struct Epilogue {
   const float* row_scale;  // [M] or null
@@ -74,11 +104,14 @@ struct Epilogue {
 };
 
 // TMEM accumulators per tile: NUM_HI for the hi*hi products (round-robin over k-steps) + 1 for the cross terms.
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
+// H2 = fp16 operand split: stage = [A raw fp32 (TMA) | A hi f16 | A lo f16 | B hi f16 | B lo f16], rows of 32 halves (SWIZZLE_64B)
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2 = false>
 struct SmemLayout {
   static constexpr int kNumAcc = NUM_HI + 1;
-  static constexpr uint32_t kBBoxBytes = BLOCK_N * BLOCK_K * 4;
-  static constexpr uint32_t kStageBytes = 2 * kABoxBytes + 2 * kBBoxBytes;
+  static constexpr uint32_t kAHalfBytes = BLOCK_M * BLOCK_K * 2;  // 8 KiB
+  static constexpr uint32_t kBBoxBytes = H2 ? BLOCK_N * BLOCK_K * 2 : BLOCK_N * BLOCK_K * 4;
+  static constexpr uint32_t kBOffset = H2 ? kABoxBytes + 2 * kAHalfBytes : 2 * kABoxBytes;  // B hi inside a stage
+  static constexpr uint32_t kStageBytes = kBOffset + 2 * kBBoxBytes;
   static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
   static constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;      // two warps per TMEM lane quarter share a tile's 32-column chunks
   static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;   // per epilogue warp: one 32 x 32 fp32 tile for TMA stores
@@ -87,6 +120,8 @@ struct SmemLayout {
   static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
   static constexpr uint32_t kTmemCols = ACC_BUFS * kNumAcc * BLOCK_N;  // ACC_BUFS = 2: double-buffered accumulators
   static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
+  static_assert(kTotal <= 232448, "shared memory budget of one CTA");
+  static_assert(kStageBytes % 1024 == 0 && kBOffset % 1024 == 0 && kBBoxBytes % 1024 == 0, "swizzled boxes stay 1024-byte aligned");
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
@@ -100,14 +135,14 @@ struct SmemLayout {
 // consecutive k-steps rotate over three accumulators; the epilogue adds them in fp32 round-to-nearest.
 // ACC_BUFS = 1 (long reductions with wide tiles: 4 accumulators x 128 columns fill TMEM) trades the epilogue / mainloop
 // overlap — a few per cent of a K > 1024 mainloop — for 128-column MMAs, which halve the shared-memory reads of A per flop.
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
 __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo,
                                                           const __grid_constant__ CUtensorMap map_c,
                                                           const __grid_constant__ CUtensorMap map_o2, float* __restrict__ C,
                                                           int64_t M, int N, int K, int ldc, Epilogue ep) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>;
   constexpr int kNumAcc = L::kNumAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -164,15 +199,15 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           const uint32_t st = base + (uint32_t)s * L::kStageBytes;
           mbar_expect_tx(full_bar(s), kABoxBytes + 2 * L::kBBoxBytes);
           tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, m0);
-          tma_load_2d(st + 2 * kABoxBytes, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
-          tma_load_2d(st + 2 * kABoxBytes + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
+          tma_load_2d(st + L::kBOffset, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
+          tma_load_2d(st + L::kBOffset + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = H2 ? make_instr_desc_f16(BLOCK_M, BLOCK_N) : make_instr_desc(BLOCK_M, BLOCK_N);
       uint32_t it = 0, lt = 0;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt % ACC_BUFS;
@@ -185,6 +220,18 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           mbar_wait(split_bar(s), (it / STAGES) & 1u);
           tcgen05_fence_after();
           const uint32_t st = base + (uint32_t)s * L::kStageBytes;
+          if constexpr (H2) {
+            const uint64_t a_hi = make_smem_desc_sw64(st + kABoxBytes), a_lo = make_smem_desc_sw64(st + kABoxBytes + L::kAHalfBytes);
+            const uint64_t b_hi = make_smem_desc_sw64(st + L::kBOffset), b_lo = make_smem_desc_sw64(st + L::kBOffset + L::kBBoxBytes);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k-step inside the 64-byte swizzle row
+              const int ks = kb * (BLOCK_K / 16) + k;
+              umma_f16(acc_x, a_lo + adv, b_hi + adv, idesc, ks != 0 ? 1u : 0u);
+              umma_f16(acc_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(acc0 + (uint32_t)(ks % NUM_HI) * BLOCK_N, a_hi + adv, b_hi + adv, idesc, ks >= NUM_HI ? 1u : 0u);
+            }
+          } else {
           const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kABoxBytes);
           const uint64_t b_hi = make_smem_desc(st + 2 * kABoxBytes), b_lo = make_smem_desc(st + 2 * kABoxBytes + L::kBBoxBytes);
 #pragma unroll
@@ -194,6 +241,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
             umma_tf32(acc_x, a_lo + adv, b_hi + adv, idesc, ks != 0 ? 1u : 0u);
             umma_tf32(acc_x, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32(acc0 + (uint32_t)(ks % NUM_HI) * BLOCK_N, a_hi + adv, b_hi + adv, idesc, ks >= NUM_HI ? 1u : 0u);
+          }
           }
           umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
         }
@@ -208,6 +256,32 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = (int)(it % STAGES);
         mbar_wait(full_bar(s), (it / STAGES) & 1u);
+        if constexpr (H2) {
+          // raw fp32 box (128 rows x 128 B, SWIZZLE_128B as TMA wrote it) -> fp16 hi / lo boxes (128 rows x 64 B, SWIZZLE_64B).
+          // float4 f of the raw box = row f / 8, physical 16-byte chunk f % 8 = logical chunk (f % 8) ^ (row % 8), i.e.
+          // k = 4 c .. 4 c + 3; its four halves land in logical 16-byte chunk c / 2 (physical (c / 2) ^ ((row / 2) % 4)) at
+          // byte (c % 2) * 8.  Consecutive threads read consecutive float4 and write into one 64-byte row: conflict-free.
+          const float4* raw = reinterpret_cast<const float4*>(base_ptr + (size_t)s * L::kStageBytes);
+          uint8_t* hi8 = base_ptr + (size_t)s * L::kStageBytes + kABoxBytes;
+          uint8_t* lo8 = hi8 + L::kAHalfBytes;
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = raw[t + 128 * j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int f = t + 128 * j;
+            const int r = f >> 3, c = (f & 7) ^ (r & 7);
+            const uint32_t o = (uint32_t)r * 64u + (uint32_t)(((c >> 1) ^ ((r >> 1) & 3)) << 4) + (uint32_t)((c & 1) << 3);
+            __half h0, h1, h2, h3, l0, l1, l2, l3;
+            split_h2(v[j].x, h0, l0);
+            split_h2(v[j].y, h1, l1);
+            split_h2(v[j].z, h2, l2);
+            split_h2(v[j].w, h3, l3);
+            const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+            *reinterpret_cast<uint2*>(hi8 + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+            *reinterpret_cast<uint2*>(lo8 + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+          }
+        } else {
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes);
         float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::kStageBytes + kABoxBytes);
         float4 v[8];
@@ -222,6 +296,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           split_tf32_fast(v[j].w, h.w, l.w);
           hi[t + 128 * j] = h;
           lo[t + 128 * j] = l;
+        }
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -297,14 +372,16 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           tmem_ld_32x32b_x32(acc0 + (uint32_t)c0, r);
           tmem_ld_32x32b_x32(acc0 + (uint32_t)(BLOCK_N + c0), r2);
           tmem_ld_wait();
+          // the cross-term accumulator is the LAST one; the fp16 split keeps it scaled by 2^11
+          constexpr float kX = H2 ? kLoUnscale : 1.0f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]) * (kNumAcc == 2 ? kX : 1.0f);
           if constexpr (kNumAcc == 4) {
             tmem_ld_32x32b_x32(acc0 + (uint32_t)(2 * BLOCK_N + c0), r);
             tmem_ld_32x32b_x32(acc0 + (uint32_t)(3 * BLOCK_N + c0), r2);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]) * kX;
           }
         }
         // row scale, column scale / shift (same addresses in every lane: broadcast loads, L1 resident)
@@ -463,6 +540,21 @@ __global__ void __launch_bounds__(256) k_split_weights(const float* __restrict__
   }
 }
 
+// The same for the fp16 split: hi / lo as __half [N, ldb] (ldb a multiple of 8 halves).
+__global__ void __launch_bounds__(256) k_split_weights_h2(const float* __restrict__ w, int k_dim, int n_dim, int ldb, int transpose,
+                                                          __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t total = (int64_t)n_dim * ldb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ldb), k = (int)(i - (int64_t)n * ldb);
+    float v = 0.f;
+    if (k < k_dim) v = transpose ? w[(int64_t)k * n_dim + n] : w[(int64_t)n * k_dim + k];
+    __half h, l;
+    split_h2(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -498,25 +590,51 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int64_t
   return KPREG_OK;
 }
 
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS>
+// 2-D fp16 tensor [rows, cols] with row pitch ld (halves), box = [box_rows, 32 halves], SWIZZLE_64B (the fp16-split weights)
+int make_map_h(CUtensorMap* map, const __half* ptr, int64_t rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return KPREG_E_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
+    return KPREG_E_CUDA;
+  }
+  return KPREG_OK;
+}
+
+// Operand format of the tensor-core GEMM for this process: fp16 split (default) or 3xTF32 (KPREG_GEMM_TF32=1).  The
+// pre-split weight buffers are in the matching format, so the choice is made once.
+bool gemm_h2() {
+  static const bool h2 = [] { const char* e = getenv("KPREG_GEMM_TF32"); return !(e && e[0] == '1'); }();
+  return h2;
+}
+
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
 int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
                        const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>;
   static PerDeviceOnce once;  // (the attribute is per device: a second GPU in the same process needs its own call)
   const int rc_cfg = once.run([]() -> int {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     return KPREG_OK;
   });
   if (rc_cfg) return rc_cfg;
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
 
 int ldb_for(int k_dim) { return (k_dim + 3) / 4 * 4; }
+int ldb_h_for(int k_dim) { return (k_dim + 7) / 8 * 8; }  // halves: rows stay 16-byte aligned
 int npad_for(int n_dim) { return (n_dim + 15) / 16 * 16; }
 
 }  // namespace
@@ -532,6 +650,17 @@ bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a) {
 
 // Split the weights: w is [kd, n] (transpose = 1) or [n, kd] (transpose = 0).  w_split holds hi then lo.
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream) {
+  if (gemm_h2()) {
+    const int ldb = ldb_h_for(kd);
+    __half* hi = reinterpret_cast<__half*>(w_split);
+    __half* lo = hi + (size_t)npad_for(n) * ldb;
+    const int64_t total = (int64_t)n * ldb;
+    int blocks = ceil_div(total, 256);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    k_split_weights_h2<<<blocks, 256, 0, stream>>>(weights, kd, n, ldb, transpose, hi, lo);
+    KP_LAUNCH_CHECK();
+    return KPREG_OK;
+  }
   const int ldb = ldb_for(kd);
   float* hi = w_split;
   float* lo = w_split + (size_t)npad_for(n) * ldb;
@@ -549,6 +678,7 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
                    int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
                    int post_act, cudaStream_t stream) {
   if (!gemm_tc_supported(m, kd, n, lda, a)) return KPREG_E_INVALID;
+  const bool h2 = gemm_h2();
   const int ldb = ldb_for(kd);
   const float* hi = w_split;
   const float* lo = w_split + (size_t)npad_for(n) * ldb;
@@ -561,10 +691,19 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   CUtensorMap ma, mbh, mbl;
   int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&mbh, hi, n, kd, ldb, block_n);
-  if (rc) return rc;
-  rc = make_map(&mbl, lo, n, kd, ldb, block_n);
-  if (rc) return rc;
+  if (h2) {
+    const int ldh = ldb_h_for(kd);
+    const __half* hh = reinterpret_cast<const __half*>(w_split);
+    rc = make_map_h(&mbh, hh, n, kd, ldh, block_n);
+    if (rc) return rc;
+    rc = make_map_h(&mbl, hh + (size_t)npad_for(n) * ldh, n, kd, ldh, block_n);
+    if (rc) return rc;
+  } else {
+    rc = make_map(&mbh, hi, n, kd, ldb, block_n);
+    if (rc) return rc;
+    rc = make_map(&mbl, lo, n, kd, ldb, block_n);
+    if (rc) return rc;
+  }
   auto aligned = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0); };
   const int vec_ok = aligned(c, ldc) && aligned(residual, ld_res) && aligned(out2, ld2) && aligned(addend, ld_add) && aligned(post_res, ld_post);
   // outputs leave through TMA when every pointer / pitch is 16-byte aligned (the store clips at M and N itself)
@@ -577,14 +716,24 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   if (rc) return rc;
   Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, tma_store,
               post_res, ld_post, post_act};
-  if (num_hi == 3) {
-    if (block_n == 32) return launch_tile_config<32, 3, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    if (block_n == 64) return launch_tile_config<64, 3, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    return launch_tile_config<128, 3, 3, 1>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (h2) {
+    if (num_hi == 3) {
+      if (block_n == 32) return launch_tile_config<32, 3, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      if (block_n == 64) return launch_tile_config<64, 3, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      return launch_tile_config<128, 3, 4, 1, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    }
+    if (block_n == 32) return launch_tile_config<32, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 64) return launch_tile_config<64, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
   }
-  if (block_n == 32) return launch_tile_config<32, 1, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  if (block_n == 64) return launch_tile_config<64, 1, 4, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  return launch_tile_config<128, 1, 3, 2>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (num_hi == 3) {
+    if (block_n == 32) return launch_tile_config<32, 3, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 64) return launch_tile_config<64, 3, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 3, 3, 1, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  }
+  if (block_n == 32) return launch_tile_config<32, 1, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 1, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 1, 3, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
 }
 
 }  // namespace kpreg
