@@ -687,7 +687,11 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   // wide outputs of long reductions: 128-column tiles with single-buffered accumulators (4 x 128 TMEM columns)
   static const bool no_wide3 = [] { const char* e = getenv("KPREG_GEMM_NO_WIDE3"); return e && e[0] == '1'; }();
   const bool wide3 = num_hi == 3 && n > 64 && !no_wide3;
-  const int block_n = n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128);
+  // fp16 split, K <= 1024, wide outputs: 128 x 256 tiles (two single-buffered 256-column accumulators fill TMEM) — the
+  // mainloop is bound by shared-memory bandwidth and a 256-column MMA reads A once for twice the output
+  static const bool no_n256 = [] { const char* e = getenv("KPREG_GEMM_NO_N256"); return e && e[0] == '1'; }();
+  const bool n256 = h2 && num_hi == 1 && n >= 256 && kd >= 256 && !no_n256;
+  const int block_n = n256 ? 256 : (n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128));
   CUtensorMap ma, mbh, mbl;
   int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
   if (rc) return rc;
@@ -722,6 +726,7 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
       if (block_n == 64) return launch_tile_config<64, 3, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
       return launch_tile_config<128, 3, 4, 1, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     }
+    if (block_n == 256) return launch_tile_config<256, 1, 3, 1, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     if (block_n == 32) return launch_tile_config<32, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     if (block_n == 64) return launch_tile_config<64, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     return launch_tile_config<128, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
