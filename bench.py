@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("KPREG_BENCH_CLOCK_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -489,11 +489,17 @@ def main():
 
     def timed(fn, steps, warmup, profile):
         if profile:
-            _lib.profile(True)  # warm-up also warms the library's CUDA-event pool (no cudaEventCreate in the timed region)
+            _lib.profile(True)
         for _ in range(warmup):
             fn()
             flush.fill_(1)
         torch.cuda.synchronize()
+        # The per-family CUDA events are recorded in the first `prof_steps` steps of the timed region only: thousands of
+        # pending event pairs slow the stream down (measured: 7 000 scopes over 20 steps cost 5 ms per step, 1 750 nothing).
+        prof_steps = min(5, steps) if profile else 0
+        if profile:
+            per_step = sum(v[1] for v in _lib.profile_read().values()) // max(warmup, 1) + 8
+            _lib.profile_reserve(per_step * (prof_steps + 1))  # their events exist before the timed region starts
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -504,6 +510,8 @@ def main():
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         last = None
         for i in range(steps):
+            if profile and i == prof_steps:
+                _lib.profile(False)  # stops recording; the records stay readable
             starts[i].record()
             last = fn()
             ends[i].record()
@@ -515,7 +523,10 @@ def main():
         fam = _lib.profile_read() if profile else None
         if profile:
             _lib.profile(False)
-        ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+            fam = {k: (v[0] * steps / prof_steps, v[1] * steps / prof_steps) for k, v in fam.items()}  # scaled to `steps` steps
+        per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        timed.last_steps = [round(v, 2) for v in per_step_ms]
+        ms = sum(per_step_ms)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -530,12 +541,14 @@ def main():
         path(b0.src_dev, b0.tgt_dev, b0.poses_dev, corr=b0.corr)
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KPREG_BENCH_NO_CLOCKS") else None
     if sampler:
         sampler.start()
     ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True)
+    steps_resident = timed.last_steps
     clocks = sampler.stop() if sampler else None
     ms_e2e, _, _, last_e2e = timed(step_e2e, args.steps, args.warmup, profile=False)
+    steps_e2e = timed.last_steps
 
     value = n_global * args.steps / (ms_total / 1000.0) if args.scaling == "strong" else n_local * world * args.steps / (ms_total / 1000.0)
     e2e_value = value * ms_total / ms_e2e
@@ -647,6 +660,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_copies_per_step": 2 * len(my_batches)},
             "gpu_launches": int(launches),
+            "step_ms": {"resident": steps_resident, "e2e": steps_e2e},
             "roofline": roof,
             "cpu_baseline": cpu,
             "parity_check": parity,

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "kpreg_last_error": (ctypes.c_char_p, []),
     "kpreg_launch_count": (ctypes.c_ulonglong, []),
     "kpreg_profile": (_c_int, [_c_int]),
+    "kpreg_profile_reserve": (_c_int, [_c_int]),
     "kpreg_profile_read": (_c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]),
     "kpreg_subsample_workspace_bytes": (_c_int, [_c_i64, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_subsample_batch": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_f32, _c_int, _c_ptr, _c_ptr,
@@ -136,6 +137,11 @@ FAMILIES = ("subsample", "grid_build", "grid_query", "kpconv_gather", "kpconv_co
 def profile(enable: bool) -> None:
     """Start (and clear) / stop per-kernel-family device timing."""
     check(load().kpreg_profile(1 if enable else 0), "kpreg_profile")
+
+
+def profile_reserve(n_records: int) -> None:
+    """Pre-create the CUDA events of ``n_records`` timed scopes (so that a measured region creates none)."""
+    check(load().kpreg_profile_reserve(int(n_records)), "kpreg_profile_reserve")
 
 
 def profile_read() -> Dict[str, Tuple[float, int]]:

@@ -51,6 +51,19 @@ extern "C" int kpreg_profile(int enable) {
   return KPREG_OK;
 }
 
+// Pre-create the CUDA events of `n_records` timed scopes, so that a measured region creates none.
+extern "C" int kpreg_profile_reserve(int n_records) {
+  std::lock_guard<std::mutex> lock(kpreg::g_prof_mutex);
+  while ((int)kpreg::g_prof_pool.size() < n_records) {
+    kpreg::ProfRecord r;
+    KP_CUDA_TRY(cudaEventCreate(&r.begin));
+    KP_CUDA_TRY(cudaEventCreate(&r.end));
+    r.family = -1;
+    kpreg::g_prof_pool.push_back(r);
+  }
+  return KPREG_OK;
+}
+
 extern "C" int kpreg_profile_read(double* ms, unsigned long long* launches) {
   if (!ms || !launches) return KPREG_E_INVALID;
   std::lock_guard<std::mutex> lock(kpreg::g_prof_mutex);

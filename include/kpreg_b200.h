@@ -60,6 +60,7 @@ KPREG_API unsigned long long kpreg_launch_count(void);
 #define KPREG_FAM_NORM 9        /* kpreg_segment_norm_forward */
 #define KPREG_N_FAMILIES 10
 KPREG_API int kpreg_profile(int enable);
+KPREG_API int kpreg_profile_reserve(int n_records);  /* pre-create the events of n_records timed scopes */
 KPREG_API int kpreg_profile_read(double* ms /*[KPREG_N_FAMILIES]*/, unsigned long long* launches /*[KPREG_N_FAMILIES]*/);
 
 /* ---------------------------------------------------------------------------------------------
