@@ -36,6 +36,8 @@ import torch  # noqa: E402
 
 METRIC = "point-cloud pairs/sec (subsample+neighbours+KPConv+Kabsch)"
 UNIT = "pairs/s"
+# operand split of the tcgen05 GEMMs (csrc/kpconv_gemm.cu gemm_h2()): fp16 hi + 2^11-scaled fp16 lo by default, 3xTF32 on request
+SPLIT_NAME = "3xTF32 split" if os.environ.get("KPREG_GEMM_TF32", "")[:1] == "1" else "fp16 hi/lo split (3 products, fp32 accumulate)"
 WORKLOAD = "3DMatch-shape synthetic pairs (~20k pts/cloud, voxel 0.025 m, 4-level KPConv pyramid)"
 
 
@@ -374,7 +376,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --pairs per GPU per step; strong: --global-pairs per step sharded round-robin over the GPUs (SURVEY §8d config 5)")
     ap.add_argument("--global-pairs", type=int, default=512)
-    ap.add_argument("--gemm", type=int, default=None, help="contractions: 0 fp32 CUDA cores, 1 tcgen05 3xTF32 (default)")
+    ap.add_argument("--gemm", type=int, default=None, help="contractions: 0 fp32 CUDA cores, 1 tcgen05 split-operand GEMM (default; fp16 hi/lo split, or 3xTF32 under KPREG_GEMM_TF32=1)")
     ap.add_argument("--no-fused-glue", action="store_true", help="run the block glue on stock PyTorch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the ModelNet / MCD / training-step side measurements")
@@ -566,8 +568,8 @@ def main():
                   "linear": work["linear_bytes"], "kpconv_contract": None}[top]
         names = {"kpconv_gather": "k_kpconv_gather_mma + k_kpconv_c1 (KPConv gather + influence + aggregation)",
                  "grid_query": "k_grid_query_tq / k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
-                 "linear": "k_gemm_tc + k_chain (block Linear layers: tcgen05 3xTF32 GEMMs, register-resident res2net chain)",
-                 "kpconv_contract": "k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 3xTF32)"}
+                 "linear": f"k_gemm_tc + k_chain (block Linear layers: tcgen05 {SPLIT_NAME} GEMMs, register-resident res2net chain)",
+                 "kpconv_contract": f"k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 {SPLIT_NAME})"}
         if top == "kpconv_contract":
             ach = work["contract_flops"] / (fam_ms[top] * 1e-3) / 1e12
             roof = {"kernel": names[top], "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -594,7 +596,8 @@ def main():
         }
         fams["frac_of_hbm"] = {k[:-4]: round(fams[k] / hbm, 4) for k in ("kpconv_gather_GBs", "linear_GBs", "grid_query_GBs", "segment_norm_GBs", "subsample_GBs")}
         if tf32:
-            # 3xTF32: three tensor-core products per fp32-equivalent product
+            # split operands: three tensor-core products per fp32-equivalent product (the fp16 split issues kind::f16 MMAs, whose
+            # dense peak is twice TF32's — the TF32 figure is kept as the common denominator)
             fams["kpconv_contract_frac_of_tf32_peak"] = {"fp32_equivalent": round(fams["kpconv_contract_TFLOPs"] / tf32, 4),
                                                           "issued_3x": round(3 * fams["kpconv_contract_TFLOPs"] / tf32, 4), "tf32_peak_TFLOPs": tf32}
         roof["families"] = fams
@@ -649,7 +652,7 @@ def main():
                        "sub_batch_pairs": args.pairs,
                        "points_per_level": [int(p.shape[0]) for p in out["meta"]["points"]],
                        "neighbor_widths": [int(t.shape[1]) for t in out["meta"]["neighbors"]],
-                       "kpconv_contraction": "tcgen05-3xTF32" if kpconv_blocks.DEFAULT_GEMM == 1 else "fp32-cuda-core",
+                       "kpconv_contraction": f"tcgen05 {SPLIT_NAME}" if kpconv_blocks.DEFAULT_GEMM == 1 else "fp32-cuda-core",
                        "block_glue": "fused CUDA (tcgen05 linear + segment norm)" if kpconv_blocks.FUSED_GLUE else "PyTorch ops",
                        "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective; all-gather of [P,14] poses+errors per step",
                        "kabsch_inputs": "decoder-shaped synthetic correspondences (the decoder is out of scope), built once from the batch's "
