@@ -65,6 +65,10 @@ _SIGNATURES = {
     "kpreg_chain_pack": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr]),
     "kpreg_chain_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_ptr, _c_int, _c_int,
                                      _c_ptr]),
+    "kpreg_front_supported": (_c_int, [_c_int, _c_int, _c_int]),
+    "kpreg_front_pack_bytes": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "kpreg_front_pack": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_front_forward": (_c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_int, _c_i64, _c_ptr, _c_int, _c_int, _c_ptr]),
     "kpreg_kabsch": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f32, _c_int, _c_ptr, _c_ptr]),
     "kpreg_overlap_pool": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_i64, _c_i64, _c_int, _c_ptr, _c_ptr]),
     "kpreg_sine_embed": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_f32, _c_ptr, _c_ptr, _c_ptr]),

@@ -56,34 +56,7 @@ constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 
 using namespace tc;  // PTX wrappers (tc_ptx.cuh)
 
-// ---- fp16 operand split (H2 variant) ---------------------------------------------------------------------------
-// x = hi + lo' * 2^-11 with hi = fp16(x) (11 significant bits, like TF32) and lo' = fp16((x - hi) * 2^11): 22 bits in all —
-// the same budget as the 3xTF32 split — but `kind::f16` runs at twice the TF32 rate, an operand element is 2 bytes instead
-// of 4 (the mainloop is bound by shared-memory bandwidth) and K is 16 per instruction.  The cross terms are accumulated
-// unscaled in their own TMEM accumulator and scaled by 2^-11 in the epilogue.  Range: |x| < 65504 (fp16); magnitudes
-// below 6e-5 keep an absolute accuracy of 6e-8.  KPREG_GEMM_TF32=1 selects the TF32 kernel instead.
-constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
-__device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
-}
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 32 halves): 8-row groups 512 B apart, version 1.
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t addr) {
-  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
-}
-// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, shape M x N x 16.
-__device__ __forceinline__ uint32_t make_instr_desc_f16(int m, int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// (the fp16 operand split helpers — split_h2, SWIZZLE_64B descriptors, kind::f16 MMA — live in tc_ptx.cuh)
 
 struct Epilogue {
   const float* row_scale;  // [M] or null

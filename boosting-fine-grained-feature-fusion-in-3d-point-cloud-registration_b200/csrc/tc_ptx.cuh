@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace kpreg {
@@ -105,6 +106,81 @@ __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// 1-D bulk copy global -> shared (multiples of 16 bytes, 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(x),
+               "r"(y), "r"(z)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// ---- fp16 operand split (H2 variant) ---------------------------------------------------------------------------
+// x = hi + lo' * 2^-11 with hi = fp16(x) (11 significant bits, like TF32) and lo' = fp16((x - hi) * 2^11): 22 bits in all —
+// the same budget as the 3xTF32 split — but `kind::f16` runs at twice the TF32 rate, an operand element is 2 bytes instead
+// of 4 (the mainloop is bound by shared-memory bandwidth) and K is 16 per instruction.  The cross terms are accumulated
+// unscaled in their own TMEM accumulator and scaled by 2^-11 in the epilogue.  Range: |x| < 65504 (fp16); magnitudes
+// below 6e-5 keep an absolute accuracy of 6e-8.  KPREG_GEMM_TF32=1 selects the TF32 kernel instead.
+constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
+}
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 32 halves): 8-row groups 512 B apart, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, shape M x N x 16.
+__device__ __forceinline__ uint32_t make_instr_desc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+
+// ---- host: tensor maps -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFnT encode_tiled_fn() {
+  static EncodeTiledFnT fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnT>(p);
+  }
+  return fn;
+}
+// fp32 tensor of `rank` dimensions (innermost first): dims, byte strides of dimensions 1.., box.  Returns false on failure.
+inline bool encode_f32_map(CUtensorMap* map, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                           const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFnT fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 }  // namespace tc
 }  // namespace kpreg

@@ -35,6 +35,10 @@ DEFAULT_GEMM = 1
 FUSED_GLUE = True
 # res2net's chained layers in one register-resident kernel (kpreg_chain_forward) where the width allows it
 CHAIN_KERNEL = True
+# conv1 + the chained layers in one tcgen05 kernel (kpreg_front_forward) where width / input channels allow it
+# (KPREG_NO_FRONT=1: conv1 as its own GEMM + the chain kernel, for A/B runs)
+import os as _os
+FRONT_KERNEL = _os.environ.get("KPREG_NO_FRONT", "")[:1] != "1"
 
 
 def _fused(x: torch.Tensor) -> bool:

@@ -551,6 +551,42 @@ def chain_forward(t: torch.Tensor, pack: ChainPack, z: torch.Tensor, x_copy: Opt
     return z
 
 
+class FrontPack:
+    """conv1 and chain weights of a res2net unit (BatchNorm folded in) as the operand boxes kpreg_front_forward copies."""
+
+    def __init__(self, w1: torch.Tensor, b1: torch.Tensor, wc: torch.Tensor, bc: torch.Tensor):
+        lib = _lib.load()
+        w1, b1, wc, bc = _f32c(w1, "w1"), _f32c(b1, "b1"), _f32c(wc, "wc"), _f32c(bc, "bc")
+        self.width, self.n_groups, self.c_in = int(wc.shape[1]), int(wc.shape[0]) + 1, int(w1.shape[1])
+        if (tuple(w1.shape) != (self.n_groups * self.width, self.c_in) or tuple(b1.shape) != (self.n_groups * self.width,)
+                or tuple(wc.shape) != (self.n_groups - 1, self.width, self.width) or tuple(bc.shape) != (self.n_groups - 1, self.width)):
+            raise RuntimeError("front: w1 [G w, c_in], b1 [G w], wc [G-1, w, w], bc [G-1, w] expected")
+        nbytes = _lib.size_query("kpreg_front_pack_bytes", self.width, self.n_groups, self.c_in)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=w1.device)
+        rc = lib.kpreg_front_pack(w1.data_ptr(), b1.data_ptr(), wc.data_ptr(), bc.data_ptr(), self.width, self.n_groups, self.c_in,
+                                  self.buf.data_ptr(), nbytes, _lib.stream_ptr(w1.device))
+        _lib.check(rc, "kpreg_front_pack")
+
+
+def front_supported(width: int, n_groups: int, c_in: int) -> bool:
+    return bool(_lib.load().kpreg_front_supported(int(width), int(n_groups), int(c_in)))
+
+
+@_on_tensor_device
+def front_forward(x: torch.Tensor, pack: FrontPack, z: torch.Tensor, copy_x: bool = False) -> torch.Tensor:
+    """conv1 + the chained layers of a res2net unit over x [M, c_in] into z [M, >= G w (+ c_in)] (kpreg_front_forward)."""
+    lib = _lib.load()
+    x, ld_x = _rows(x, "x")
+    _lib.require_cuda(z, "z")
+    if z.dtype != torch.float32 or z.dim() != 2 or z.stride(1) != 1 or x.shape[1] != pack.c_in or z.shape[0] != x.shape[0]:
+        raise RuntimeError("front: x [M, c_in] and a float32 z [M, >= G w] with contiguous rows expected")
+    m = x.shape[0]
+    rc = lib.kpreg_front_forward(x.data_ptr(), ld_x, pack.c_in, pack.buf.data_ptr(), pack.width, pack.n_groups, m, z.data_ptr(),
+                                 int(z.stride(0)) if m > 1 else int(z.shape[1]), 1 if copy_x else 0, _lib.stream_ptr(x.device))
+    _lib.check(rc, "kpreg_front_forward")
+    return z
+
+
 # ------------------------------------------------------------------------------------------------
 # the steps on either side of the path: overlap pyramid, coarse-level packing, point shuffling
 # ------------------------------------------------------------------------------------------------

@@ -76,6 +76,18 @@ class my_Bottle2neck(_CacheInvalidating):
             self._kpreg_chain = cache
         return cache[1]
 
+    def _front_pack(self):
+        """Folded conv1 / bn1 and convs[i] / bns[i] as the operand boxes of kpreg_front_forward (cached like _chain_pack)."""
+        from . import ops
+        w1, b1 = _folded(self.conv1, self.bn1)
+        folded = [_folded(self.convs[i], self.bns[i]) for i in range(self.nums)]
+        key = (self.bn1._kpreg_folded[0],) + tuple(self.bns[i]._kpreg_folded[0] for i in range(self.nums))
+        cache = getattr(self, "_kpreg_front", None)
+        if cache is None or cache[0] != key:
+            cache = (key, ops.FrontPack(w1, b1, torch.stack([f[0] for f in folded]), torch.stack([f[1] for f in folded])))
+            self._kpreg_front = cache
+        return cache[1]
+
     def _fused_forward(self, x, shortcut=None):
         """Inference on CUDA: every Linear + eval-BatchNorm (+ ReLU) is one tensor-core GEMM with a fused
         epilogue; the chained layers run in one register-resident kernel where the width allows it (otherwise
@@ -87,12 +99,21 @@ class my_Bottle2neck(_CacheInvalidating):
         w, n_groups = self.width, self.scale
         gemm = kb.DEFAULT_GEMM
         wt, sh = _folded(self.conv1, self.bn1)
-        t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm)                      # [N, w * scale]
         fuse_res = self.downsample is not None and x.shape[1] % 4 == 0
         k_cat = w * n_groups
-        z = torch.empty((t.shape[0], k_cat + (x.shape[1] if fuse_res else 0)), dtype=t.dtype, device=t.device)
-        chain = kb.CHAIN_KERNEL and self.nums == n_groups - 1 and ops.chain_supported(w, self.nums)
-        if chain:
+        z = torch.empty((x.shape[0], k_cat + (x.shape[1] if fuse_res else 0)), dtype=x.dtype, device=x.device)
+        front = (kb.FRONT_KERNEL and gemm == 1 and self.nums == n_groups - 1 and x.dtype == torch.float32 and x.stride(1) == 1
+                 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and ops.front_supported(w, n_groups, x.shape[1]))
+        chain = front or (kb.CHAIN_KERNEL and self.nums == n_groups - 1 and ops.chain_supported(w, self.nums))
+        if front:
+            # conv1 and all chained layers in one tcgen05 kernel: conv1's output never leaves the SM
+            ops.front_forward(x, self._front_pack(), z, copy_x=fuse_res)
+            t = None
+        else:
+            t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm)                  # [N, w * scale]
+        if front:
+            pass
+        elif chain:
             # all chained layers in one kernel: a warp keeps its rows of the running activation in registers,
             # t is read once, z written once (the pass-through group and the copy of x included)
             ops.chain_forward(t, self._chain_pack(), z, x if fuse_res else None)

@@ -240,6 +240,28 @@ KPREG_API int kpreg_chain_forward(const float* t, int ld_t, const void* pack, in
                                   float* z, int ld_z, const float* x_copy, int ld_x, int c_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * conv1 + bn1 + relu AND the hierarchical chain of my_Bottle2neck in one tcgen05 kernel
+ * (models/backbone_kpconv/res2net.py:125-152): per 128-row tile, group by group,
+ *     t_g = relu(x W1_g^T + b1_g),   y_0 = relu(t_0 Wc_0^T + bc_0),   y_g = relu((y_{g-1} + t_g) Wc_g^T + bc_g)
+ * and z = [y_0 | ... | y_{G-2} | t_{G-1} | x (when copy_x)].  conv1's output and the running activation stay on the SM
+ * (TMEM accumulators, fp16 hi/lo operand boxes in shared memory): x is read once, z written once.
+ *   kpreg_front_supported: 1 if (width, n_groups, c_in) is served: width % 4 == 0, 2 <= n_groups <= 8, c_in % 4 == 0 and
+ *       either 16 <= width <= 32 with c_in <= 32 (all weights resident in shared memory, two CTAs per SM) or
+ *       32 < width <= 64 with c_in <= 64 (weights streamed per group from L2).  Else 0: the caller runs conv1 through
+ *       kpreg_linear_forward and the chain through kpreg_chain_forward.
+ *   kpreg_front_pack: w1 [n_groups*width, c_in] and wc [n_groups-1, width, width] (nn.Linear layout [out, in], BN scale folded
+ *       in), b1 [n_groups*width], bc [n_groups-1, width] -> the operand boxes the kernel copies (kpreg_front_pack_bytes bytes).
+ *   kpreg_front_forward: x [M, ld_x] (c_in columns), z [M, ld_z]; ld_x, ld_z multiples of 4, bases 16-byte aligned,
+ *       ld_z >= n_groups*width (+ c_in when copy_x).  Operands are split into fp16 pairs: |value| < 65504.
+ * ------------------------------------------------------------------------------------------- */
+KPREG_API int kpreg_front_supported(int width, int n_groups, int c_in);
+KPREG_API int kpreg_front_pack_bytes(int width, int n_groups, int c_in, size_t* bytes);
+KPREG_API int kpreg_front_pack(const float* w1, const float* b1, const float* wc, const float* bc, int width, int n_groups,
+                               int c_in, void* pack, size_t pack_bytes, void* stream);
+KPREG_API int kpreg_front_forward(const float* x, int ld_x, int c_in, const void* pack, int width, int n_groups,
+                                  int64_t m_rows, float* z, int ld_z, int copy_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The steps on either side of the path.
  *
  * kpreg_overlap_pool: one level of compute_overlaps()   models/backbone_kpconv/finegrained_kpconv.py:545-571

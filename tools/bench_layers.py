@@ -68,7 +68,13 @@ def d_chain(_res, t, pack, z, x_copy=None):
     return f"M={m} w={pack.width} L={pack.n_layers}", 4 * m * (2 * g + (2 * x_copy.shape[1] if x_copy is not None else 0))
 
 
+def d_front(_res, x, pack, z, copy_x=False):
+    m, c = x.shape
+    return f"M={m} c_in={c} w={pack.width} G={pack.n_groups}", 4 * m * (c + pack.n_groups * pack.width + (c if copy_x else 0))
+
+
 ops.chain_forward = wrap("chain", ops.chain_forward, d_chain)
+ops.front_forward = wrap("front", ops.front_forward, d_front)
 ops.linear_forward = wrap("linear", ops.linear_forward, d_linear)
 ops.segment_norm = wrap("segnorm", ops.segment_norm, d_norm)
 ops.kpconv_forward = wrap("kpconv", ops.kpconv_forward, d_kpconv)
