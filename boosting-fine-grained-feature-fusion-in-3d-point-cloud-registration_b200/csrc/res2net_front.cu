@@ -43,7 +43,7 @@ constexpr int kFrontWorkers = 8;
 constexpr int kFrontThreads = 32 * (kFrontWorkers + 2);
 constexpr int kFrontMaxGroups = 8;
 
-template <int WP, int K1, bool STREAM>
+template <int WP, int K1>
 struct FrontLayout {
   static constexpr int NKX = K1 / 32, NKA = WP / 32;
   static constexpr int CW = WP / 2;                                  // columns of a group per worker thread
@@ -54,39 +54,39 @@ struct FrontLayout {
   static constexpr uint32_t kW1 = 2 * NKX * WP * 64;                 // one group's conv1 weights: hi boxes [WP x 32 halves], then lo
   static constexpr uint32_t kWc = 2 * NKA * WP * 64;                 // one group's chain weights
   static constexpr uint32_t kBlob = kW1 + kWc;
-  static constexpr int kWStages = STREAM ? 2 : kFrontMaxGroups;
-  static constexpr uint32_t kW = kWStages * kBlob - (STREAM ? 0 : kWc);  // resident: the last group has no chain layer
-  static constexpr uint32_t kStgWarp = 32 * CW * 4;                  // one [32 rows x CW floats] tile per worker warp
-  static constexpr uint32_t kStg = kFrontWorkers * kStgWarp;
-  static constexpr bool kAlias = !STREAM;                            // the staging tiles reuse the raw x box (two CTAs per SM)
+  static constexpr int kWStages = WP == 32 ? 3 : 2;                  // ring of per-group weight blobs (streamed from L2)
+  static constexpr uint32_t kW = kWStages * kBlob;
+  static constexpr int kStgBufs = WP == 32 ? 2 : 1;                  // staging tiles per worker warp
+  static constexpr uint32_t kStgTile = 32 * CW * 4;                  // one [32 rows x CW floats] tile
+  static constexpr uint32_t kStg = kFrontWorkers * kStgBufs * kStgTile;
   static constexpr uint32_t kShift = 2 * kFrontMaxGroups * WP * 4;   // b1 [8][WP], bc [8][WP]
   static constexpr uint32_t oXRaw = 0;
   static constexpr uint32_t oXSplit = oXRaw + kXRaw;
   static constexpr uint32_t oA = oXSplit + kXSplit;
   static constexpr uint32_t oW = oA + kA;
-  static constexpr uint32_t oStg = kAlias ? oXRaw : oW + kW;
-  static constexpr uint32_t oShift = kAlias ? oW + kW : oStg + kStg;
+  static constexpr uint32_t oStg = oW + kW;
+  static constexpr uint32_t oShift = oStg + kStg;
   static constexpr uint32_t oBar = oShift + kShift;
   static constexpr uint32_t kTotal = oBar + 256 + 1024;              // + slack for the 1024-byte alignment
+  static constexpr int kCtasPerSm = kTotal <= 115712u ? 2 : 1;
   static constexpr uint32_t kTmemCols = 4 * WP;                      // conv1 hi*hi, conv1 cross, chain hi*hi, chain cross
   static constexpr size_t kPackBytes = (size_t)kFrontMaxGroups * kBlob + kShift;
   static_assert(WP == 32 || WP == 64, "group width padded to 32 or 64 columns");
-  static_assert(!kAlias || kStg <= kXRaw, "staging tiles must fit the raw x box they alias");
-  static_assert(kBlob % 1024 == 0 && kW1 % 1024 == 0 && oW % 1024 == 0 && oStg % 1024 == 0 && kStgWarp % 1024 == 0,
+  static_assert(kBlob % 1024 == 0 && kW1 % 1024 == 0 && oW % 1024 == 0 && oStg % 1024 == 0 && kStgTile % 1024 == 0,
                 "swizzled boxes stay 1024-byte aligned");
-  static_assert(kTotal <= (STREAM ? 232448u : 115712u), "shared memory budget (one / two CTAs per SM)");
+  static_assert(kTotal <= 232448u, "shared memory budget of one CTA");
 };
 
-enum FrontBar { kXFull = 0, kXEmpty, kXsFull, kXcDone, kTFull, kTEmpty, kAFull, kCFull, kWFull0, kWFull1, kWEmpty0, kWEmpty1, kNumBars };
+enum FrontBar { kXFull = 0, kXEmpty, kXsFull, kTFull, kTEmpty, kAFull, kCFull, kWFull0, kWEmpty0 = kWFull0 + 4, kNumBars = kWEmpty0 + 4 };
 
-template <int WP, int K1, bool STREAM>
-__global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front(const __grid_constant__ CUtensorMap map_x,
+template <int WP, int K1>
+__global__ void __launch_bounds__(kFrontThreads, FrontLayout<WP, K1>::kCtasPerSm) k_res2net_front(const __grid_constant__ CUtensorMap map_x,
                                                                                   const __grid_constant__ CUtensorMap map_z,
                                                                                   const __grid_constant__ CUtensorMap map_xc,
                                                                                   const uint8_t* __restrict__ pack, int n_groups,
                                                                                   int64_t m_rows, int copy_x) {
-  using L = FrontLayout<WP, K1, STREAM>;
-  constexpr int NKX = L::NKX, NKA = L::NKA, CW = L::CW;
+  using L = FrontLayout<WP, K1>;
+  constexpr int NKX = L::NKX, NKA = L::NKA, CW = L::CW, WS = L::kWStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -105,15 +105,14 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
     mbar_init(bar(kXFull), 1);
     mbar_init(bar(kXEmpty), kFrontWorkers);
     mbar_init(bar(kXsFull), kFrontWorkers);
-    mbar_init(bar(kXcDone), 1);
     mbar_init(bar(kTFull), 1);
     mbar_init(bar(kTEmpty), kFrontWorkers);
     mbar_init(bar(kAFull), kFrontWorkers);
     mbar_init(bar(kCFull), 1);
-    mbar_init(bar(kWFull0), 1);
-    mbar_init(bar(kWFull1), 1);
-    mbar_init(bar(kWEmpty0), 1);
-    mbar_init(bar(kWEmpty1), 1);
+    for (int i = 0; i < WS; ++i) {
+      mbar_init(bar(kWFull0 + i), 1);
+      mbar_init(bar(kWEmpty0 + i), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -132,18 +131,14 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
   if (warp == 9) {
     // ---------------- producer
     if (lane == 0 && blockIdx.x < num_tiles) {
-      if constexpr (!STREAM) {
-        mbar_expect_tx(bar(kWFull0), (uint32_t)n_layers * L::kBlob + L::kW1);
-        for (int g = 0; g < n_groups; ++g)
-          bulk_load_1d(base + L::oW + (uint32_t)g * L::kBlob, pack + (size_t)g * L::kBlob, g < n_layers ? L::kBlob : L::kW1, bar(kWFull0));
-      }
       auto load_x = [&](uint32_t tile) {
         mbar_expect_tx(bar(kXFull), L::kXRaw);
         for (int b = 0; b < NKX; ++b) tma_load_2d(base + L::oXRaw + (uint32_t)b * 16384u, &map_x, bar(kXFull), b * 32, (int)tile * kFrontRows);
       };
+      // group g's weights into ring slot ws % WS (ws counts groups across this CTA's tiles)
       auto load_w = [&](uint32_t ws, int g) {
-        const uint32_t s = ws & 1u;
-        mbar_wait(bar(kWEmpty0 + (int)s), ((ws >> 1) & 1u) ^ 1u);
+        const uint32_t s = ws % WS;
+        mbar_wait(bar(kWEmpty0 + (int)s), ((ws / WS) & 1u) ^ 1u);
         mbar_expect_tx(bar(kWFull0 + (int)s), L::kBlob);
         bulk_load_1d(base + L::oW + s * L::kBlob, pack + (size_t)g * L::kBlob, L::kBlob, bar(kWFull0 + (int)s));
       };
@@ -155,19 +150,15 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
           mbar_wait(bar(kXFull), lt & 1u);
           for (int b = 0; b < NKX; ++b) tma_store_2d(&map_xc, base + L::oXRaw + (uint32_t)b * 16384u, b * 32, (int)tile * kFrontRows);
           tma_store_wait_read();
-          if constexpr (L::kAlias) mbar_arrive(bar(kXcDone));
         }
         const uint32_t ws0 = lt * (uint32_t)n_groups;
-        if constexpr (STREAM) {
-          for (int g = 0; g < 2 && g < n_groups; ++g) load_w(ws0 + (uint32_t)g, g);
-        }
+        const int first = n_groups < WS ? n_groups : WS;
+        for (int g = 0; g < first; ++g) load_w(ws0 + (uint32_t)g, g);
         if (tile + gridDim.x < num_tiles) {
-          mbar_wait(bar(kXEmpty), lt & 1u);  // the workers are done with this tile's raw box (and, aliased, with their staging tiles)
+          mbar_wait(bar(kXEmpty), lt & 1u);  // the workers have split this tile's raw box: the next tile's load may land
           load_x(tile + gridDim.x);
         }
-        if constexpr (STREAM) {
-          for (int g = 2; g < n_groups; ++g) load_w(ws0 + (uint32_t)g, g);
-        }
+        for (int g = first; g < n_groups; ++g) load_w(ws0 + (uint32_t)g, g);
       }
       tma_store_wait_all();
     }
@@ -191,21 +182,20 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
           }
         }
       };
-      if constexpr (!STREAM) mbar_wait(bar(kWFull0), 0u);
       uint32_t lt = 0;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t ts0 = lt * (uint32_t)n_groups, tc0 = lt * (uint32_t)n_layers;
         mbar_wait(bar(kXsFull), lt & 1u);
         tcgen05_fence_after();
-        auto w_base = [&](int g) { return base + L::oW + (STREAM ? ((ts0 + (uint32_t)g) & 1u) : (uint32_t)g) * L::kBlob; };
+        auto w_base = [&](int g) { return base + L::oW + ((ts0 + (uint32_t)g) % WS) * L::kBlob; };
         auto conv1 = [&](int g) {
           const uint32_t ts = ts0 + (uint32_t)g;
           mbar_wait(bar(kTEmpty), (ts & 1u) ^ 1u);  // the workers have read the previous group's accumulator
-          if constexpr (STREAM) mbar_wait(bar(kWFull0 + (int)(ts & 1u)), (ts >> 1) & 1u);
+          mbar_wait(bar(kWFull0 + (int)(ts % WS)), (ts / WS) & 1u);
           tcgen05_fence_after();
           issue(base + L::oXSplit, w_base(g), NKX, t_hh, t_x);
           umma_commit(bar(kTFull));
-          if (STREAM && g == n_groups - 1) umma_commit(bar(kWEmpty0 + (int)(ts & 1u)));  // the last group has no chain layer
+          if (g == n_groups - 1) umma_commit(bar(kWEmpty0 + (int)(ts % WS)));  // the last group has no chain layer
         };
         conv1(0);
         for (int g = 0; g < n_layers; ++g) {
@@ -214,7 +204,7 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
           tcgen05_fence_after();
           issue(base + L::oA, w_base(g) + L::kW1, NKA, c_hh, c_x);
           umma_commit(bar(kCFull));
-          if constexpr (STREAM) umma_commit(bar(kWEmpty0 + (int)((ts0 + (uint32_t)g) & 1u)));
+          umma_commit(bar(kWEmpty0 + (int)((ts0 + (uint32_t)g) % WS)));
         }
       }
     }
@@ -224,8 +214,8 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
     const int c0 = hcol * CW;
     const int row = 32 * q + lane;  // row of the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
-    uint8_t* stg_ptr = base_ptr + L::oStg + (uint32_t)warp * L::kStgWarp;
-    const uint32_t stg = base + L::oStg + (uint32_t)warp * L::kStgWarp;
+    const uint32_t stg_off = L::oStg + (uint32_t)warp * (L::kStgBufs * L::kStgTile);
+    uint32_t n_stores = 0;  // staging tiles alternate when the warp has two
     const float* s_b1 = s_shift;
     const float* s_bc = s_shift + kFrontMaxGroups * WP;
     const int tid = threadIdx.x;  // 0 .. 255
@@ -246,8 +236,15 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
     };
     // v -> this warp's swizzled staging tile -> one TMA store into group `grp` of z (clipped at the group's width and at M)
     auto store_tile = [&](const float (&v)[CW], int grp, int m0) {
-      if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the tile
+      const uint32_t off = stg_off + (L::kStgBufs == 2 ? (n_stores & 1u) * L::kStgTile : 0u);
+      ++n_stores;
+      // the store that last used this tile has finished reading it
+      if (lane == 0) {
+        if constexpr (L::kStgBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else tma_store_wait_read();
+      }
       __syncwarp();
+      uint8_t* stg_ptr = base_ptr + off;
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
         const int pj = CW == 32 ? (j ^ (lane & 7)) : (j ^ ((lane >> 1) & 3));
@@ -255,7 +252,7 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) tma_store_3d(&map_z, stg, c0, grp, m0 + 32 * q);
+      if (lane == 0) tma_store_3d(&map_z, base + off, c0, grp, m0 + 32 * q);
     };
 
     uint32_t lt = 0;
@@ -290,12 +287,7 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(kXsFull));
-        if constexpr (!L::kAlias) mbar_arrive(bar(kXEmpty));
-      }
-      if constexpr (L::kAlias) {
-        // the staging tiles overlay the raw box: every warp (and the producer's x copy) must be done reading it
-        mbar_wait(bar(kXsFull), lt & 1u);
-        if (copy_x) mbar_wait(bar(kXcDone), lt & 1u);
+        mbar_arrive(bar(kXEmpty));
       }
 
       float y[CW];
@@ -317,7 +309,6 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
           load_acc((uint32_t)(2 * WP + c0), y);
 #pragma unroll
           for (int j = 0; j < CW; ++j) y[j] = fmaxf(y[j] + s_bc[(g - 1) * WP + c0 + j], 0.f);
-          store_tile(y, g - 1, m0);
           if (g < n_groups - 1) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) t[j] += y[j];
@@ -346,15 +337,10 @@ __global__ void __launch_bounds__(kFrontThreads, STREAM ? 1 : 2) k_res2net_front
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kAFull));
-        } else {
-          store_tile(t, g, m0);  // the last group passes through conv1 only
         }
-      }
-      if constexpr (L::kAlias) {
-        if (lane == 0) {
-          tma_store_wait_read();
-          mbar_arrive(bar(kXEmpty));
-        }
+        // the stores run under the chain MMA just released: chain accumulator -> operand boxes -> MMA is the critical path
+        if (g >= 1) store_tile(y, g - 1, m0);
+        if (g == n_groups - 1) store_tile(t, g, m0);  // the last group passes through conv1 only
       }
     }
     if (lane == 0) tma_store_wait_all();  // every store of this warp has landed before the CTA exits
@@ -415,25 +401,24 @@ __global__ void __launch_bounds__(256) k_front_pack(const float* __restrict__ w1
 
 struct FrontConfig {
   int wp, k1;
-  bool stream;
 };
 bool front_config(int width, int n_groups, int c_in, FrontConfig* cfg) {
   if (width < 16 || (width & 3) || n_groups < 2 || n_groups > kFrontMaxGroups || c_in < 4 || (c_in & 3)) return false;
-  if (width <= 32 && c_in <= 32) { *cfg = {32, 32, false}; return true; }
-  if (width > 32 && width <= 64 && c_in <= 64) { *cfg = {64, 64, true}; return true; }
+  if (width <= 32 && c_in <= 32) { *cfg = {32, 32}; return true; }
+  if (width > 32 && width <= 64 && c_in <= 64) { *cfg = {64, 64}; return true; }
   return false;
 }
 size_t front_pack_bytes(const FrontConfig& c) {
-  return c.stream ? FrontLayout<64, 64, true>::kPackBytes : FrontLayout<32, 32, false>::kPackBytes;
+  return c.wp == 64 ? FrontLayout<64, 64>::kPackBytes : FrontLayout<32, 32>::kPackBytes;
 }
 
-template <int WP, int K1, bool STREAM>
+template <int WP, int K1>
 int launch_front(const float* x, int ld_x, int c_in, const uint8_t* pack, int width, int n_groups, int64_t m_rows, float* z, int ld_z,
                  int copy_x, cudaStream_t stream) {
-  using L = FrontLayout<WP, K1, STREAM>;
+  using L = FrontLayout<WP, K1>;
   static PerDeviceOnce once;
   const int rc_cfg = once.run([]() -> int {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_res2net_front<WP, K1, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_res2net_front<WP, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     return KPREG_OK;
   });
   if (rc_cfg) return rc_cfg;
@@ -460,9 +445,9 @@ int launch_front(const float* x, int ld_x, int c_in, const uint8_t* pack, int wi
     memset(&mxc, 0, sizeof(mxc));
   }
   const int64_t tiles = ceil_div(m_rows, (int64_t)kFrontRows);
-  const int64_t max_ctas = (int64_t)kNumSMs * (STREAM ? 1 : 2);
+  const int64_t max_ctas = (int64_t)kNumSMs * L::kCtasPerSm;
   const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-  k_res2net_front<WP, K1, STREAM><<<grid, kFrontThreads, L::kTotal, stream>>>(mx, mz, mxc, pack, n_groups, m_rows, copy_x);
+  k_res2net_front<WP, K1><<<grid, kFrontThreads, L::kTotal, stream>>>(mx, mz, mxc, pack, n_groups, m_rows, copy_x);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -507,6 +492,6 @@ extern "C" int kpreg_front_forward(const float* x, int ld_x, int c_in, const voi
   cudaStream_t stream = (cudaStream_t)stream_;
   ProfScope prof(KPREG_FAM_LINEAR, stream);
   const uint8_t* pk = static_cast<const uint8_t*>(pack);
-  if (c.stream) return launch_front<64, 64, true>(x, ld_x, c_in, pk, width, n_groups, m_rows, z, ld_z, copy_x ? 1 : 0, stream);
-  return launch_front<32, 32, false>(x, ld_x, c_in, pk, width, n_groups, m_rows, z, ld_z, copy_x ? 1 : 0, stream);
+  if (c.wp == 64) return launch_front<64, 64>(x, ld_x, c_in, pk, width, n_groups, m_rows, z, ld_z, copy_x ? 1 : 0, stream);
+  return launch_front<32, 32>(x, ld_x, c_in, pk, width, n_groups, m_rows, z, ld_z, copy_x ? 1 : 0, stream);
 }
