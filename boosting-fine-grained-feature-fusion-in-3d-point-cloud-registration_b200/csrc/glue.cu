@@ -71,7 +71,7 @@ __device__ __forceinline__ void stat_flush(double* __restrict__ stats, int cloud
 }
 
 // stats[(cloud * C + ch) * 2 + {0,1}] += {sum x, sum x^2} in fp64.  Each thread streams float4 (4 channels) of 16
-// rows; a CTA covers 256 rows x 64 channels and issues one atomic pair per channel when it lies inside one cloud.
+// rows; a CTA covers 256 rows x 64 channels and issues one atomic pair per channel and cloud segment of its rows.
 // TX = threads per row (8 for rows of <= 32 channels: no idle lanes), 256 / TX row groups.
 template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
@@ -85,11 +85,14 @@ __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__
   const int c_first = cloud_of(off, n_clouds, r0);
   const int c_last = cloud_of(off, n_clouds, r1 - 1);
   const bool live = ch < channels;  // channels is a multiple of 4
-  double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
-  if (c_first == c_last) {
+  // one pass per cloud segment of the chunk (coarse levels: clouds of a few hundred rows, most chunks hold two or three):
+  // per-thread partial sums -> shared-memory reduction over the row groups -> one atomic pair per channel and segment
+  for (int c = c_first; c <= c_last; ++c) {
+    const int64_t s0 = max(r0, off[c]), s1 = min(r1, off[c + 1]);
+    double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
     if (live) {
 #pragma unroll 4
-      for (int64_t r = r0 + ry; r < r1; r += RY) {
+      for (int64_t r = s0 + ry; r < s1; r += RY) {
         const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
         sum[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
         sum[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
@@ -97,38 +100,21 @@ __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__
         sum[3] += (double)v.w; sq[3] += (double)v.w * (double)v.w;
       }
     }
+    if (c != c_first) __syncthreads();  // the previous segment's reduction has read the tiles
 #pragma unroll
     for (int e = 0; e < 4; ++e) { s_sum[ry][cx * 4 + e] = sum[e]; s_sq[ry][cx * 4 + e] = sq[e]; }
     __syncthreads();
-    if (threadIdx.x < CH) {
-      const int c = blockIdx.y * CH + threadIdx.x;
-      if (c < channels) {
+    if (threadIdx.x < CH && s1 > s0) {
+      const int cc = blockIdx.y * CH + threadIdx.x;
+      if (cc < channels) {
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int g = 0; g < RY; ++g) { a += s_sum[g][threadIdx.x]; b += s_sq[g][threadIdx.x]; }
-        double* dst = stats + ((int64_t)c_first * channels + c) * 2;
+        double* dst = stats + ((int64_t)c * channels + cc) * 2;
         atomicAdd(dst, a);
         atomicAdd(dst + 1, b);
       }
     }
-  } else if (live) {
-    // chunk straddles a cloud boundary: flush per thread whenever the cloud changes
-    int c = -1;
-    for (int64_t r = r0 + ry; r < r1; r += RY) {
-      const int cr = cloud_of(off, n_clouds, r);
-      if (cr != c) {
-        if (c >= 0) stat_flush(stats, c, channels, ch, sum, sq);
-        c = cr;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sum[e] = sq[e] = 0.0;
-      }
-      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
-      sum[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
-      sum[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
-      sum[2] += (double)v.z; sq[2] += (double)v.z * (double)v.z;
-      sum[3] += (double)v.w; sq[3] += (double)v.w * (double)v.w;
-    }
-    if (c >= 0) stat_flush(stats, c, channels, ch, sum, sq);
   }
 }
 
@@ -168,15 +154,17 @@ __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__
     if (c < 0 || r >= c_end) {
       c = cloud_of(off, n_clouds, r);
       c_end = off[c + 1];
-      const double n = (double)max((int64_t)1, c_end - off[c]);
+      // (one fp64 division per cloud change; the moments and the cancellation-prone E[x^2] - mean^2 stay in fp64, the
+      // reciprocal square root runs in fp32 — at the coarse levels a thread changes cloud every few rows)
+      const double inv_n = 1.0 / (double)max((int64_t)1, c_end - off[c]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const double* st = stats + ((int64_t)c * channels + ch + e) * 2;
-        const double m = st[0] / n;
-        double var = st[1] / n - m * m;
+        const double m = st[0] * inv_n;
+        double var = st[1] * inv_n - m * m;
         if (var < 0.0) var = 0.0;
         mean[e] = (float)m;
-        rstd[e] = (float)(1.0 / sqrt(var + (double)eps));
+        rstd[e] = 1.0f / sqrtf((float)(var + (double)eps));
       }
     }
     const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
