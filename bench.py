@@ -568,7 +568,7 @@ def main():
                   "linear": work["linear_bytes"], "kpconv_contract": None}[top]
         names = {"kpconv_gather": "k_kpconv_gather_mma + k_kpconv_c1 (KPConv gather + influence + aggregation)",
                  "grid_query": "k_grid_query_tq / k_grid_query (radius neighbours)", "subsample": "subsample_batch (all kernels)",
-                 "linear": f"k_gemm_tc + k_chain (block Linear layers: tcgen05 {SPLIT_NAME} GEMMs, register-resident res2net chain)",
+                 "linear": f"k_gemm_tc + k_res2net_front (block Linear layers: tcgen05 {SPLIT_NAME} GEMMs; conv1 + chain of the narrow res2net units in one tcgen05 kernel)",
                  "kpconv_contract": f"k_gemm_tc (KPConv contraction [Nq,K*Cin]x[K*Cin,Cout], tcgen05 {SPLIT_NAME})"}
         if top == "kpconv_contract":
             ach = work["contract_flops"] / (fam_ms[top] * 1e-3) / 1e12
@@ -604,7 +604,7 @@ def main():
         # DRAM traffic of the family from the committed ncu capture of this build (dram__bytes_read.sum + dram__bytes_write.sum
         # over one step's launches), scaled to this run's pairs per step
         tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
-        fam_kernels = {"linear": ("k_gemm_tc", "k_chain"), "kpconv_contract": ("k_gemm_tc",),
+        fam_kernels = {"linear": ("k_gemm_tc", "k_chain", "k_res2net_front"), "kpconv_contract": ("k_gemm_tc",),
                        "kpconv_gather": ("k_kpconv_gather_mma", "k_kpconv_c1"), "grid_query": ("k_grid_query",)}.get(top)
         if os.path.exists(tpath) and fam_kernels:
             tr = json.load(open(tpath))

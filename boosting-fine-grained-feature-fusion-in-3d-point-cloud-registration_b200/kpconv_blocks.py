@@ -38,7 +38,8 @@ CHAIN_KERNEL = True
 # conv1 + the chained layers in one tcgen05 kernel (kpreg_front_forward) where width / input channels allow it
 # (KPREG_NO_FRONT=1: conv1 as its own GEMM + the chain kernel, for A/B runs)
 import os as _os
-FRONT_KERNEL = _os.environ.get("KPREG_NO_FRONT", "")[:1] != "1"
+# (the front kernel always splits operands into fp16 pairs: under KPREG_GEMM_TF32=1 — fp32 range — it is not used)
+FRONT_KERNEL = _os.environ.get("KPREG_NO_FRONT", "")[:1] != "1" and _os.environ.get("KPREG_GEMM_TF32", "")[:1] != "1"
 
 
 def _fused(x: torch.Tensor) -> bool:

@@ -6,7 +6,7 @@ import json
 import sys
 from collections import defaultdict
 
-FAMILIES = ("k_gemm_tc", "k_gemm_tn", "k_chain", "k_max_pool", "k_segnorm", "k_kpconv_gather_mma", "k_kpconv_c1", "k_grid_query_tq",
+FAMILIES = ("k_gemm_tc", "k_gemm_tn", "k_chain", "k_res2net_front", "k_max_pool", "k_segnorm", "k_kpconv_gather_mma", "k_kpconv_c1", "k_grid_query_tq",
             "k_grid_query", "k_order", "k_row_positive", "k_pack_coarse", "k_overlap_pool")
 with open(sys.argv[1], newline="") as fh:
     lines = [l for l in fh if not l.startswith("==")]
