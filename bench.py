@@ -80,6 +80,10 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=10)  # its NVML teardown stalls CUDA calls of every process for ~0.2 s: keep it out of the next region
+        except Exception:
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:

@@ -18,6 +18,10 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
                    const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
                    int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
                    int post_act, cudaStream_t stream);
+int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int lda2, const float* w_split, float* c, int ldc, int64_t m,
+                        int kd, int n, const float* row_scale, const float* col_scale, const float* col_shift, const float* residual,
+                        int ld_res, int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res,
+                        int ld_post, int post_act, cudaStream_t stream);
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
@@ -306,6 +310,20 @@ extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight
                                               slope, out, ldc, out2, ld2, addend, ld_add, post_residual, ld_post, post_act);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
+}
+
+extern "C" int kpreg_linear_pair_forward(const float* x1, int ld1, int k1, const float* x2, int ld2, int k2, const float* w_split,
+                                         int64_t m_rows, int n_dim, const float* col_scale, const float* col_shift, int act,
+                                         float slope, float* out, int ldc, void* stream_) {
+  if (m_rows < 0 || k1 < 4 || k2 < 1 || n_dim < 8 || ld1 < k1 || ld2 < k2 || ldc < n_dim || act < 0 || act > 2) return KPREG_E_INVALID;
+  if (m_rows == 0) return KPREG_OK;
+  if (!x1 || !x2 || !w_split || !out) return KPREG_E_INVALID;
+  const int kd = (k1 + 31) / 32 * 32 + k2;
+  if (!gemm_tc_supported(m_rows, kd, n_dim, ld1, x1)) return KPREG_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ProfScope prof(KPREG_FAM_LINEAR, stream);
+  return launch_gemm_tc_pair(x1, ld1, k1, x2, ld2, w_split, out, ldc, m_rows, kd, n_dim, nullptr, col_scale, col_shift, nullptr, 0, act,
+                             slope, nullptr, 0, nullptr, 0, nullptr, 0, 0, stream);
 }
 
 extern "C" int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes) {

@@ -110,6 +110,7 @@ struct SmemLayout {
 // overlap — a few per cent of a K > 1024 mainloop — for 128-column MMAs, which halve the shared-memory reads of A per flop.
 template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
 __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+                                                          const __grid_constant__ CUtensorMap map_a2, int kb_split,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo,
                                                           const __grid_constant__ CUtensorMap map_c,
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_a2);
     tma_prefetch_desc(&map_b_hi);
     tma_prefetch_desc(&map_b_lo);
     for (int s = 0; s < STAGES; ++s) {
@@ -171,7 +173,10 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
           const uint32_t st = base + (uint32_t)s * L::kStageBytes;
           mbar_expect_tx(full_bar(s), kABoxBytes + 2 * L::kBBoxBytes);
-          tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, m0);
+          // k-blocks [0, kb_split) come from A, the rest from a second row-major operand (K-concatenated inputs that live
+          // in different tensors: [A | A2] * [W1 | W2]^T without materialising the concatenation)
+          if (kb < kb_split) tma_load_2d(st, &map_a, full_bar(s), kb * BLOCK_K, m0);
+          else tma_load_2d(st, &map_a2, full_bar(s), (kb - kb_split) * BLOCK_K, m0);
           tma_load_2d(st + L::kBOffset, &map_b_hi, full_bar(s), kb * BLOCK_K, n0);
           tma_load_2d(st + L::kBOffset + L::kBBoxBytes, &map_b_lo, full_bar(s), kb * BLOCK_K, n0);
         }
@@ -589,7 +594,7 @@ bool gemm_h2() {
 }
 
 template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
-int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
+int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& ma2, int kb_split, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
                        const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>;
   static PerDeviceOnce once;  // (the attribute is per device: a second GPU in the same process needs its own call)
@@ -601,7 +606,7 @@ int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& mbh, const CUte
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, ma2, kb_split, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -645,12 +650,29 @@ int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int tran
   return KPREG_OK;
 }
 
+int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int lda2, const float* w_split, float* c, int ldc, int64_t m,
+                        int kd, int n, const float* row_scale, const float* col_scale, const float* col_shift, const float* residual,
+                        int ld_res, int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res,
+                        int ld_post, int post_act, cudaStream_t stream);
+
 // C[m, n] (row pitch ldc) = epilogue(A[m, kd] (row pitch lda) * Bt^T) with pre-split weights.
 int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int ldc, int64_t m, int kd, int n,
                    const float* row_scale, const float* col_scale, const float* col_shift, const float* residual, int ld_res,
                    int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res, int ld_post,
                    int post_act, cudaStream_t stream) {
+  return launch_gemm_tc_pair(a, lda, kd, nullptr, 0, w_split, c, ldc, m, kd, n, row_scale, col_scale, col_shift, residual, ld_res, act, slope,
+                             out2, ld2, addend, ld_add, post_res, ld_post, post_act, stream);
+}
+
+// The same with the reduction index split over two row-major operands: columns [0, k1) of the product's K come from a
+// (k1 valid columns, zero-filled up to the next multiple of 32), columns [pad32(k1), kd) from a2.  a2 == nullptr: plain GEMM.
+int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int lda2, const float* w_split, float* c, int ldc, int64_t m,
+                        int kd, int n, const float* row_scale, const float* col_scale, const float* col_shift, const float* residual,
+                        int ld_res, int act, float slope, float* out2, int ld2, const float* addend, int ld_add, const float* post_res,
+                        int ld_post, int post_act, cudaStream_t stream) {
   if (!gemm_tc_supported(m, kd, n, lda, a)) return KPREG_E_INVALID;
+  const int k1_pad = (k1 + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  if (a2 && (k1 < 4 || k1_pad >= kd || (lda2 % 4) != 0 || (reinterpret_cast<uintptr_t>(a2) % 16) != 0)) return KPREG_E_INVALID;
   const bool h2 = gemm_h2();
   const int ldb = ldb_for(kd);
   const float* hi = w_split;
@@ -665,9 +687,12 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
   static const bool no_n256 = [] { const char* e = getenv("KPREG_GEMM_NO_N256"); return e && e[0] == '1'; }();
   const bool n256 = h2 && num_hi == 1 && n >= 256 && kd >= 256 && !no_n256;
   const int block_n = n256 ? 256 : (n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128));
-  CUtensorMap ma, mbh, mbl;
-  int rc = make_map(&ma, a, m, kd, lda, BLOCK_M);
+  CUtensorMap ma, ma2, mbh, mbl;
+  int rc = make_map(&ma, a, m, a2 ? k1 : kd, lda, BLOCK_M);
   if (rc) return rc;
+  rc = make_map(&ma2, a2 ? a2 : a, m, a2 ? kd - k1_pad : kd, a2 ? lda2 : lda, BLOCK_M);
+  if (rc) return rc;
+  const int kb_split = a2 ? k1_pad / BLOCK_K : (1 << 30);
   if (h2) {
     const int ldh = ldb_h_for(kd);
     const __half* hh = reinterpret_cast<const __half*>(w_split);
@@ -695,23 +720,23 @@ int launch_gemm_tc(const float* a, int lda, const float* w_split, float* c, int 
               post_res, ld_post, post_act};
   if (h2) {
     if (num_hi == 3) {
-      if (block_n == 32) return launch_tile_config<32, 3, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-      if (block_n == 64) return launch_tile_config<64, 3, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-      return launch_tile_config<128, 3, 4, 1, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      if (block_n == 32) return launch_tile_config<32, 3, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      if (block_n == 64) return launch_tile_config<64, 3, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      return launch_tile_config<128, 3, 4, 1, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
     }
-    if (block_n == 256) return launch_tile_config<256, 1, 3, 1, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    if (block_n == 32) return launch_tile_config<32, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    if (block_n == 64) return launch_tile_config<64, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    return launch_tile_config<128, 1, 4, 2, true>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 256) return launch_tile_config<256, 1, 3, 1, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 32) return launch_tile_config<32, 1, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 64) return launch_tile_config<64, 1, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 1, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
   }
   if (num_hi == 3) {
-    if (block_n == 32) return launch_tile_config<32, 3, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    if (block_n == 64) return launch_tile_config<64, 3, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-    return launch_tile_config<128, 3, 3, 1, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 32) return launch_tile_config<32, 3, 4, 2, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    if (block_n == 64) return launch_tile_config<64, 3, 4, 2, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 3, 3, 1, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
   }
-  if (block_n == 32) return launch_tile_config<32, 1, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  if (block_n == 64) return launch_tile_config<64, 1, 4, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
-  return launch_tile_config<128, 1, 3, 2, false>(ma, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 32) return launch_tile_config<32, 1, 4, 2, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  if (block_n == 64) return launch_tile_config<64, 1, 4, 2, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  return launch_tile_config<128, 1, 3, 2, false>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
 }
 
 }  // namespace kpreg

@@ -418,6 +418,47 @@ def linear_forward(x, weight, col_scale=None, col_shift=None, residual=None, act
     return out
 
 
+def pair_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[W | zero columns up to a multiple of 32 | W] for ``linear_pair_forward`` with the same matrix on both inputs."""
+    n, k = weight.shape
+    pad = (-k) % 32
+    return torch.cat([weight, weight.new_zeros((n, pad)), weight], 1).contiguous()
+
+
+def linear_pair_supported(x1: torch.Tensor, x2: torch.Tensor, n: int) -> bool:
+    """The TMA addressing rule of kpreg_linear_pair_forward: fp32 row slices, 16-byte aligned bases and row pitches."""
+    ok = True
+    for t in (x1, x2):
+        ok = ok and (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+                     and t.data_ptr() % 16 == 0)
+    return bool(ok and x1.shape[0] == x2.shape[0] and x1.shape[0] > 0 and x1.shape[1] >= 4 and n >= 8)
+
+
+@_on_tensor_device
+def linear_pair_forward(x1, x2, weight_cat, col_shift=None, act=None, slope: float = 0.1, out=None, col_scale=None):
+    """act(([x1 | x2] @ weight_cat.T) * col_scale + col_shift) with the two inputs read where they lie
+    (kpreg_linear_pair_forward); weight_cat = [W1 | 0 .. | W2] with W1 padded to a multiple of 32 columns."""
+    lib = _lib.load()
+    _lib.require_cuda(x1, "x1")
+    m, k1 = x1.shape
+    k2 = x2.shape[1]
+    n = weight_cat.shape[0]
+    if weight_cat.shape[1] != (k1 + 31) // 32 * 32 + k2 or not linear_pair_supported(x1, x2, n):
+        raise RuntimeError("linear_pair: inconsistent shapes or unaligned inputs")
+    split = cached_split(weight_cat, False)
+    dev = x1.device
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=dev)
+    ldc = int(out.stride(0)) if m > 1 else max(int(out.stride(0)), n)
+    cs = None if col_scale is None else _f32c(col_scale, "col_scale")
+    cb = None if col_shift is None else _f32c(col_shift, "col_shift")
+    rc = lib.kpreg_linear_pair_forward(x1.data_ptr(), int(x1.stride(0)) if m > 1 else k1, k1, x2.data_ptr(),
+                                       int(x2.stride(0)) if m > 1 else k2, k2, split.buf.data_ptr(), m, n, _lib.ptr(cs), _lib.ptr(cb),
+                                       ACT[act], float(slope), out.data_ptr(), ldc, _lib.stream_ptr(dev))
+    _lib.check(rc, "kpreg_linear_pair_forward")
+    return out
+
+
 @_on_tensor_device
 def linear_backward(x, grad_out, weight, need_dx: bool = True, need_dw: bool = True):
     """(dx [M,K] or None, d_weight [N,K] or None) of y = x weight^T on the tensor cores (kpreg_linear_backward).

@@ -76,6 +76,16 @@ class my_Bottle2neck(_CacheInvalidating):
             self._kpreg_chain = cache
         return cache[1]
 
+    def _pair_weight(self, i, wt):
+        """[W_i | 0 | W_i] of chain layer i for ops.linear_pair_forward, cached with the folded weight it is built from."""
+        from . import ops
+        key = self.bns[i]._kpreg_folded[0]
+        cache = getattr(self.bns[i], "_kpreg_pair", None)
+        if cache is None or cache[0] != key:
+            cache = (key, ops.pair_weight(wt))
+            self.bns[i]._kpreg_pair = cache
+        return cache[1]
+
     def _front_pack(self):
         """Folded conv1 / bn1 and convs[i] / bns[i] as the operand boxes of kpreg_front_forward (cached like _chain_pack)."""
         from . import ops
@@ -118,15 +128,24 @@ class my_Bottle2neck(_CacheInvalidating):
             # t is read once, z written once (the pass-through group and the copy of x included)
             ops.chain_forward(t, self._chain_pack(), z, x if fuse_res else None)
         else:
-            scratch = [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
+            # layer by layer.  Layer i >= 1 multiplies (out_{i-1} + t_i) by its matrix: on the tensor-core path that is ONE
+            # GEMM whose reduction runs over out_{i-1} (read from z, where layer i-1 wrote it) and then over t_i, with the
+            # matrix stacked twice along K — no `out + next group` side output, no addend read in the epilogue.
+            pair = gemm == 1 and w % 4 == 0 and self.nums > 1 and ops.linear_pair_supported(z[:, :w], t[:, w:2 * w], w)
+            scratch = None if pair else [torch.empty((t.shape[0], w), dtype=t.dtype, device=t.device) for _ in range(2)]
             inp = t[:, :w]
             for i in range(self.nums):
                 wt, sh = _folded(self.convs[i], self.bns[i])
                 nxt = i + 1 < self.nums
+                if pair and i >= 1:
+                    ops.linear_pair_forward(z[:, (i - 1) * w:i * w], t[:, i * w:(i + 1) * w], self._pair_weight(i, wt), sh,
+                                            act="relu", out=z[:, i * w:(i + 1) * w])
+                    continue
                 ops.linear_forward(inp, wt, None, sh, act="relu", out=z[:, i * w:(i + 1) * w],
-                                   out2=scratch[i & 1] if nxt else None, addend=t[:, (i + 1) * w:(i + 2) * w] if nxt else None,
-                                   gemm=gemm)
-                inp = scratch[i & 1]
+                                   out2=scratch[i & 1] if (nxt and not pair) else None,
+                                   addend=t[:, (i + 1) * w:(i + 2) * w] if (nxt and not pair) else None, gemm=gemm)
+                if not pair:
+                    inp = scratch[i & 1]
             z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
         w3, b3 = _folded(self.conv3, self.bn3)
         if fuse_res:

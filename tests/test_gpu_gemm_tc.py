@@ -220,3 +220,32 @@ def test_segment_norm_backward_matches_torch_autograd():
         keep = torch.ones(n, dtype=torch.bool)
         keep[700] = False
         assert rel_err(x.grad.cpu()[keep].numpy(), x64.grad.cpu()[keep].numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k1,k2,n", [(1000, 112, 112, 112), (70001, 224, 224, 224), (129, 28, 28, 28), (5000, 56, 40, 64), (1, 8, 4, 8)])
+def test_linear_pair_forward_vs_fp64(m, k1, k2, n):
+    """kpreg_linear_pair_forward: one GEMM whose reduction runs over two tensors (column slices of wider buffers)."""
+    from kpreg_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(m + k1 + n)
+    buf1 = torch.randn(m, k1 + 2 * ((k1 + 3) // 4 * 4), generator=g).to(dev)
+    buf2 = torch.randn(m, k2 + 8, generator=g).to(dev)
+    x1 = buf1[:, (k1 + 3) // 4 * 4:(k1 + 3) // 4 * 4 + k1]
+    x2 = buf2[:, 4:4 + k2]
+    w1 = (torch.randn(n, k1, generator=g) / k1 ** 0.5).to(dev)
+    w2 = (torch.randn(n, k2, generator=g) / k2 ** 0.5).to(dev)
+    shift = (0.2 * torch.randn(n, generator=g)).to(dev)
+    wcat = torch.cat([w1, w1.new_zeros(n, (-k1) % 32), w2], 1).contiguous()
+    out_buf = torch.full((m, n + 4), -3.0, device=dev)
+    ops.linear_pair_forward(x1, x2, wcat, shift, act="relu", out=out_buf[:, :n])
+    ref = torch.relu(x1.double() @ w1.double().t() + x2.double() @ w2.double().t() + shift.double())
+    err = (out_buf[:, :n].double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+    assert err <= 1e-4, err
+    assert (out_buf[:, n:] == -3.0).all()
+    # the chain form: same matrix on both inputs
+    wp = ops.pair_weight(w1) if k1 == k2 else None
+    if wp is not None:
+        y = ops.linear_pair_forward(x1, x2, wp)
+        ref2 = (x1.double() + x2.double()) @ w1.double().t()
+        assert (y.double() - ref2).abs().max().item() / max(ref2.abs().max().item(), 1e-30) <= 1e-4

@@ -73,7 +73,14 @@ def d_front(_res, x, pack, z, copy_x=False):
     return f"M={m} c_in={c} w={pack.width} G={pack.n_groups}", 4 * m * (c + pack.n_groups * pack.width + (c if copy_x else 0))
 
 
+def d_pair(_res, x1, x2, weight_cat, *a, **kw):
+    m, k1 = x1.shape
+    k2, n = x2.shape[1], weight_cat.shape[0]
+    return f"M={m} K={k1}+{k2} N={n} pair", 4 * m * (k1 + k2 + n)
+
+
 ops.chain_forward = wrap("chain", ops.chain_forward, d_chain)
+ops.linear_pair_forward = wrap("linear", ops.linear_pair_forward, d_pair)
 ops.front_forward = wrap("front", ops.front_forward, d_front)
 ops.linear_forward = wrap("linear", ops.linear_forward, d_linear)
 ops.segment_norm = wrap("segnorm", ops.segment_norm, d_norm)
