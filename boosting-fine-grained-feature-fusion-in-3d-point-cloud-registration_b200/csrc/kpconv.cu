@@ -41,6 +41,7 @@ constexpr int KMAX = 16;             // kernel points handled per neighbour (ref
 constexpr int KSTRIDE = 20;          // floats per neighbour row of influences in shared memory: 16-byte aligned, conflict-free float4 stores
 constexpr int kGatherWarps = 4;      // warps (= queries in flight) per CTA
 bool g_gather_mma = true;            // aggregate on mma.sync (3xTF32); false = fp32 FFMA kernel (KPREG_GATHER_FFMA=1)
+bool g_c1_by_neighbour = false;      // KPREG_C1_BY_NEIGHBOUR=1: the lane-per-neighbour c_in == 1 kernel also for 'sum' aggregation (A/B)
 bool g_no_c1 = false;                // KPREG_NO_C1=1: c_in == 1 goes through the generic gather + GEMM path (A/B measurements)
 bool g_gather_novec = false;         // KPREG_GATHER_NOVEC=1: scalar-load channel binding even for aligned rows (A/B measurements)
 
@@ -562,6 +563,90 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1(
   }
 }
 
+// The same operator with the lanes bound to (kernel point, neighbour parity) instead of neighbours — 'sum' aggregation only.
+// k_kpconv_c1 spends ~800 SASS instructions per query, of which only ~250 evaluate influences: the rest is the transposing
+// butterfly that turns "a lane per neighbour" into "a lane per kernel point" (it runs at the issue limit: 2.0 ms for 2.65 M
+// queries).  Here lanes 2k and 2k+1 own kernel point k and walk the even / odd neighbours, whose relative position and
+// feature the warp stages once in shared memory ([h] float4, broadcast reads): 12 instructions per (kernel point, neighbour)
+// and one shuffle to join the two halves — lane 2k holds kernel point k's total exactly where the output stage expects it.
+template <typename IdxT, int CPL, int INFL>
+__global__ void __launch_bounds__(kGatherWarps * 32, 8) k_kpconv_c1_kp(
+    const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
+    const float* __restrict__ kernel_points, const float* __restrict__ weights, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
+    int c_out, float extent, int influence, float* __restrict__ out, const int32_t* __restrict__ order) {
+  __shared__ float s_wt[KMAX][32 * CPL];  // weights, zero-padded: lane reads column lane + 32 cc (conflict-free)
+  __shared__ __align__(16) float4 s_nb[kGatherWarps][64];  // per warp: (rx, ry, rz, x) of the query's neighbours
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < KMAX * 32 * CPL; i += blockDim.x) {
+    const int k = i / (32 * CPL), c = i % (32 * CPL);
+    s_wt[k][c] = (k < n_kpts && c < c_out) ? weights[k * c_out + c] : 0.f;
+  }
+  __syncthreads();
+  const float inv_extent = 1.0f / extent;
+  const int kp = lane >> 1, par = lane & 1;
+  const bool kp_ok = kp < n_kpts;
+  const float kx = kp_ok ? kernel_points[3 * kp] : 0.f, ky = kp_ok ? kernel_points[3 * kp + 1] : 0.f,
+              kz = kp_ok ? kernel_points[3 * kp + 2] : 0.f;
+  const int h_a = lane, h_b = 32 + lane;
+  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  int64_t it = (int64_t)blockIdx.x * per_cta + warp;
+  // the index row of the NEXT query is fetched while the current one is processed
+  int64_t n_nx = 0, ja_nx = n_s, jb_nx = n_s;
+  if (it < it_end) {
+    n_nx = order ? (int64_t)order[it] : it;  // processing order only, never the result
+    if (h_a < n_nbrs) ja_nx = (int64_t)idx[n_nx * n_nbrs + h_a];
+    if (h_b < n_nbrs) jb_nx = (int64_t)idx[n_nx * n_nbrs + h_b];
+  }
+  float4* __restrict__ nb = s_nb[warp];
+  for (; it < it_end; it += kGatherWarps) {
+    const int64_t n = n_nx, ja = ja_nx, jb = jb_nx;
+    if (it + kGatherWarps < it_end) {
+      n_nx = order ? (int64_t)order[it + kGatherWarps] : it + kGatherWarps;
+      ja_nx = h_a < n_nbrs ? (int64_t)idx[n_nx * n_nbrs + h_a] : n_s;
+      jb_nx = h_b < n_nbrs ? (int64_t)idx[n_nx * n_nbrs + h_b] : n_s;
+    }
+    const float qx = q_pts[3 * n], qy = q_pts[3 * n + 1], qz = q_pts[3 * n + 2];
+    const bool va = ja >= 0 && ja < n_s, vb = jb >= 0 && jb < n_s;
+    // a shadow neighbour is staged with feature 0: whatever its influence, it adds nothing
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (va) pa = make_float4(s_pts[3 * ja] - qx, s_pts[3 * ja + 1] - qy, s_pts[3 * ja + 2] - qz, x[ja]);
+    if (vb) pb = make_float4(s_pts[3 * jb] - qx, s_pts[3 * jb + 1] - qy, s_pts[3 * jb + 2] - qz, x[jb]);
+    int num = __popc(__ballot_sync(0xffffffffu, va && pa.w > 0.f));
+    if (n_nbrs > 32) num += __popc(__ballot_sync(0xffffffffu, vb && pb.w > 0.f));
+    __syncwarp();  // the previous query's reads of the staging rows are done
+    nb[h_a] = pa;
+    if (h_b < 64) nb[h_b] = pb;
+    __syncwarp();
+    float acc = 0.f;
+#pragma unroll 4
+    for (int h = par; h < n_nbrs; h += 2) {
+      const float4 p = nb[h];
+      float d2;
+      const float w = influence_one<INFL>(p.x, p.y, p.z, kx, ky, kz, inv_extent, extent, influence, d2);
+      acc = fmaf(w, p.w, acc);
+    }
+    if (!kp_ok) acc = 0.f;
+    const float tot = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+    float o[CPL];
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) o[cc] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const float ak = __shfl_sync(0xffffffffu, tot, 2 * k);
+#pragma unroll
+      for (int cc = 0; cc < CPL; ++cc) o[cc] = fmaf(ak, s_wt[k][lane + 32 * cc], o[cc]);
+    }
+    const float inv = 1.0f / (float)max(num, 1);
+    float* __restrict__ orow = out + n * (int64_t)c_out;
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) {
+      const int c = lane + 32 * cc;
+      if (c < c_out) orow[c] = o[cc] * inv;
+    }
+  }
+}
+
 // d_x[idx[n,h], c] += sum_k infl[n,h,k] * d_agg[n,k,c]
 template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(kGatherWarps * 32) k_kpconv_scatter(
@@ -855,6 +940,8 @@ struct GatherModeInit {
     if (e && e[0] == '1') kpreg::g_gather_novec = true;
     e = getenv("KPREG_NO_C1");
     if (e && e[0] == '1') kpreg::g_no_c1 = true;
+    e = getenv("KPREG_C1_BY_NEIGHBOUR");
+    if (e && e[0] == '1') kpreg::g_c1_by_neighbour = true;
   }
 } g_gather_mode_init;
 }  // namespace
@@ -886,13 +973,22 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   k_kpconv_c1<IdxT, CPL, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x,               \
                                                                          kernel_points, weights, n_q, n_s, n_nbrs, n_kpts, c_out,      \
                                                                          kp_extent, influence, aggregation, out, order)
-#define KP_C1(IdxT, CPL)                                                       \
-  do {                                                                         \
-    if (influence == 1) KP_C1_(IdxT, CPL, 1); else KP_C1_(IdxT, CPL, -1);      \
+#define KP_C1K_(IdxT, CPL, INFL)                                                                                                      \
+  k_kpconv_c1_kp<IdxT, CPL, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x,            \
+                                                                            kernel_points, weights, n_q, n_s, n_nbrs, n_kpts, c_out,   \
+                                                                            kp_extent, influence, out, order)
+#define KP_C1(IdxT, CPL)                                                                      \
+  do {                                                                                        \
+    if (aggregation == 0 && !g_c1_by_neighbour) {                                             \
+      if (influence == 1) KP_C1K_(IdxT, CPL, 1); else KP_C1K_(IdxT, CPL, -1);                 \
+    } else {                                                                                  \
+      if (influence == 1) KP_C1_(IdxT, CPL, 1); else KP_C1_(IdxT, CPL, -1);                   \
+    }                                                                                         \
   } while (0)
     if (idx64) { if (c_out <= 32) KP_C1(int64_t, 1); else if (c_out <= 64) KP_C1(int64_t, 2); else KP_C1(int64_t, 4); }
     else { if (c_out <= 32) KP_C1(int32_t, 1); else if (c_out <= 64) KP_C1(int32_t, 2); else KP_C1(int32_t, 4); }
 #undef KP_C1_
+#undef KP_C1K_
 #undef KP_C1
     KP_LAUNCH_CHECK();
     return KPREG_OK;
