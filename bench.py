@@ -19,6 +19,7 @@ Printed JSON (rank 0):
 present + the torch-CPU restatement of its encoder / Kabsch) on the same workload, one pair per step.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -506,6 +507,12 @@ def main():
         if profile:
             per_step = sum(v[1] for v in _lib.profile_read().values()) // max(warmup, 1) + 8
             _lib.profile_reserve(per_step * (prof_steps + 1))  # their events exist before the timed region starts
+        # Long-lived Python objects (modules, cached packs, the batches) leave the collector's working set: a full
+        # collection in the middle of a step otherwise stalls the launching thread for 0.1-0.2 s (seen as one 70-240 ms
+        # step in ten, always at the same call count) while the GPU drains; the collector is paused for the timed steps.
+        gc.collect()
+        gc.freeze()
+        gc.disable()  # (reference counting still frees every tensor of a step at once; only cycle detection waits for the region's end)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -523,6 +530,7 @@ def main():
             ends[i].record()
             flush.fill_(i & 1)  # evict L2 between timed steps (outside the events)
         torch.cuda.synchronize()
+        gc.enable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -51,7 +51,12 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;          // floats per 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32
-constexpr int gemm_threads(int block_n) { return 64 + 128 + 32 * (block_n >= 64 ? 8 : 4); }  // TMA, MMA, 4 splitters, 4|8 epilogue warps
+// warps: TMA, MMA, 4 splitters, 4 | 8 epilogue warps.  (Measured for the A-through-TMEM variant: 8 splitters — two per TMEM
+// lane quarter, 16 of the k-block's 32 columns each — with 4 epilogue warps were 2-10 % slower than 4 + 8: the splitters do not
+// pace the long-K tiles.)
+constexpr int gemm_split_warps(bool at) { return 4; }
+constexpr int gemm_epi_warps(int block_n, bool at) { return block_n >= 64 ? 8 : 4; }
+constexpr int gemm_threads(int block_n, bool at) { return 64 + 32 * gemm_split_warps(at) + 32 * gemm_epi_warps(block_n, at); }
 constexpr uint32_t kABoxBytes = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 
 using namespace tc;  // PTX wrappers (tc_ptx.cuh)
@@ -78,21 +83,28 @@ struct Epilogue {
 
 // TMEM accumulators per tile: NUM_HI for the hi*hi products (round-robin over k-steps) + 1 for the cross terms.
 // H2 = fp16 operand split: stage = [A raw fp32 (TMA) | A hi f16 | A lo f16 | B hi f16 | B lo f16], rows of 32 halves (SWIZZLE_64B)
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2 = false>
+// AT (with H2) = the split A operand lives in tensor memory: the splitter warps write hi / lo with tcgen05.st (32 columns per
+// stage) and the MMAs take A from TMEM — the stage holds only the raw A box and B, and the MMAs read only B from shared memory.
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2 = false, bool AT = false>
 struct SmemLayout {
   static constexpr int kNumAcc = NUM_HI + 1;
   static constexpr uint32_t kAHalfBytes = BLOCK_M * BLOCK_K * 2;  // 8 KiB
   static constexpr uint32_t kBBoxBytes = H2 ? BLOCK_N * BLOCK_K * 2 : BLOCK_N * BLOCK_K * 4;
-  static constexpr uint32_t kBOffset = H2 ? kABoxBytes + 2 * kAHalfBytes : 2 * kABoxBytes;  // B hi inside a stage
+  static constexpr uint32_t kBOffset = AT ? kABoxBytes : (H2 ? kABoxBytes + 2 * kAHalfBytes : 2 * kABoxBytes);  // B hi inside a stage
   static constexpr uint32_t kStageBytes = kBOffset + 2 * kBBoxBytes;
   static constexpr uint32_t kTileBytes = STAGES * kStageBytes;
-  static constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;      // two warps per TMEM lane quarter share a tile's 32-column chunks
+  static constexpr int kSplitWarps = gemm_split_warps(AT);
+  static constexpr int kEpiWarps = gemm_epi_warps(BLOCK_N, AT);  // eight: two warps per TMEM lane quarter share a tile's 32-column chunks
   static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;   // per epilogue warp: one 32 x 32 fp32 tile for TMA stores
   static constexpr uint32_t kEpiBytes = kStoreBytes;
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kTotal = kTileBytes + kEpiBytes + kBarrierBytes + 1024;  // + slack for the 1024-byte alignment
-  static constexpr uint32_t kTmemCols = ACC_BUFS * kNumAcc * BLOCK_N;  // ACC_BUFS = 2: double-buffered accumulators
-  static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
+  static constexpr uint32_t kAccCols = ACC_BUFS * kNumAcc * BLOCK_N;  // ACC_BUFS = 2: double-buffered accumulators
+  static constexpr uint32_t kATmemCols = AT ? STAGES * BLOCK_K : 0;    // per stage: 16 columns of hi pairs, 16 of lo pairs
+  static constexpr uint32_t kTmemUsed = kAccCols + kATmemCols;
+  static constexpr uint32_t kTmemCols = kTmemUsed <= 128 ? 128 : (kTmemUsed <= 256 ? 256 : 512);
+  static_assert(kTmemUsed <= 512, "TMEM holds 512 columns");
+  static_assert(!AT || H2, "the TMEM A operand is the fp16 split");
   static_assert(kTotal <= 232448, "shared memory budget of one CTA");
   static_assert(kStageBytes % 1024 == 0 && kBOffset % 1024 == 0 && kBBoxBytes % 1024 == 0, "swizzled boxes stay 1024-byte aligned");
 };
@@ -108,15 +120,15 @@ struct SmemLayout {
 // consecutive k-steps rotate over three accumulators; the epilogue adds them in fp32 round-to-nearest.
 // ACC_BUFS = 1 (long reductions with wide tiles: 4 accumulators x 128 columns fill TMEM) trades the epilogue / mainloop
 // overlap — a few per cent of a K > 1024 mainloop — for 128-column MMAs, which halve the shared-memory reads of A per flop.
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
-__global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2, bool AT>
+__global__ void __launch_bounds__(gemm_threads(BLOCK_N, AT), 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_a2, int kb_split,
                                                           const __grid_constant__ CUtensorMap map_b_hi,
                                                           const __grid_constant__ CUtensorMap map_b_lo,
                                                           const __grid_constant__ CUtensorMap map_c,
                                                           const __grid_constant__ CUtensorMap map_o2, float* __restrict__ C,
                                                           int64_t M, int N, int K, int ldc, Epilogue ep) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT>;
   constexpr int kNumAcc = L::kNumAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     tma_prefetch_desc(&map_b_lo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(split_bar(s), 4);
+      mbar_init(split_bar(s), L::kSplitWarps);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < ACC_BUFS; ++b) {
@@ -198,7 +210,18 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           mbar_wait(split_bar(s), (it / STAGES) & 1u);
           tcgen05_fence_after();
           const uint32_t st = base + (uint32_t)s * L::kStageBytes;
-          if constexpr (H2) {
+          if constexpr (AT) {
+            const uint32_t ta = tmem_base + L::kAccCols + (uint32_t)s * BLOCK_K;  // hi pairs at +0, lo pairs at +16
+            const uint64_t b_hi = make_smem_desc_sw64(st + L::kBOffset), b_lo = make_smem_desc_sw64(st + L::kBOffset + L::kBBoxBytes);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              const int ks = kb * (BLOCK_K / 16) + k;
+              umma_f16_ta(acc_x, ta + 16u + 8u * k, b_hi + adv, idesc, ks != 0 ? 1u : 0u);
+              umma_f16_ta(acc_x, ta + 8u * k, b_lo + adv, idesc, 1u);
+              umma_f16_ta(acc0 + (uint32_t)(ks % NUM_HI) * BLOCK_N, ta + 8u * k, b_hi + adv, idesc, ks >= NUM_HI ? 1u : 0u);
+            }
+          } else if constexpr (H2) {
             const uint64_t a_hi = make_smem_desc_sw64(st + kABoxBytes), a_lo = make_smem_desc_sw64(st + kABoxBytes + L::kAHalfBytes);
             const uint64_t b_hi = make_smem_desc_sw64(st + L::kBOffset), b_lo = make_smem_desc_sw64(st + L::kBOffset + L::kBBoxBytes);
 #pragma unroll
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
         umma_commit(tmem_full_bar(buf));  // this tile's accumulators are complete
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + L::kSplitWarps) {
     // ---------------- splitters (warps 2..5)
     const int t = threadIdx.x - 64;  // 0..127
     uint32_t it = 0;
@@ -234,7 +257,37 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = (int)(it % STAGES);
         mbar_wait(full_bar(s), (it / STAGES) & 1u);
-        if constexpr (H2) {
+        if constexpr (AT) {
+          // thread = one row of the raw box (TMEM lane 32 (warp % 4) + lane): its 32 floats -> 16 columns of hi pairs and 16
+          // of 2^11-scaled lo pairs in this stage's TMEM slot.  (The MMAs of the k-block that last used the slot are complete:
+          // the producer waited for their commit before it refilled the stage.)
+          constexpr int kCols = 32 / (L::kSplitWarps / 4);  // columns of the k-block per splitter thread
+          const int q = warp & 3, r = 32 * q + lane, kh = (warp - 2) >> 2;
+          const uint8_t* rawrow = base_ptr + (size_t)s * L::kStageBytes + (size_t)r * 128;
+          uint32_t hw[kCols / 2], lw[kCols / 2];
+#pragma unroll
+          for (int j = 0; j < kCols / 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(rawrow + ((((kCols / 4) * kh + j) ^ (r & 7)) << 4));
+            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((v.x - f01.x) * kLoScale, (v.y - f01.y) * kLoScale);
+            const __half2 l23 = __floats2half2_rn((v.z - f23.x) * kLoScale, (v.w - f23.y) * kLoScale);
+            hw[2 * j] = *reinterpret_cast<const uint32_t*>(&h01);
+            hw[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            lw[2 * j] = *reinterpret_cast<const uint32_t*>(&l01);
+            lw[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + L::kAccCols + (uint32_t)s * BLOCK_K + (uint32_t)(kCols / 2) * kh;
+          if constexpr (kCols == 32) {
+            tmem_st_32x32b_x16(ta, hw);
+            tmem_st_32x32b_x16(ta + 16u, lw);
+          } else {
+            tmem_st_32x32b_x8(ta, hw);
+            tmem_st_32x32b_x8(ta + 16u, lw);
+          }
+          tmem_st_wait();
+          tcgen05_fence_before();
+        } else if constexpr (H2) {
           // raw fp32 box (128 rows x 128 B, SWIZZLE_128B as TMA wrote it) -> fp16 hi / lo boxes (128 rows x 64 B, SWIZZLE_64B).
           // float4 f of the raw box = row f / 8, physical 16-byte chunk f % 8 = logical chunk (f % 8) ^ (row % 8), i.e.
           // k = 4 c .. 4 c + 3; its four halves land in logical 16-byte chunk c / 2 (physical (c / 2) ^ ((row / 2) % 4)) at
@@ -276,7 +329,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           lo[t + 128 * j] = l;
         }
         }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        if constexpr (!AT) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(s));
       }
@@ -285,7 +338,7 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
     // ---------------- epilogue (warps 6..): warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row.  With
     // 8 epilogue warps, the two warps of a lane quarter take alternate 32-column chunks of the tile.
     const int q = warp & 3;
-    const int ew = warp - 6;                       // 0 .. kEpiWarps-1
+    const int ew = warp - (2 + L::kSplitWarps);    // 0 .. kEpiWarps-1
     const int half = ew >> 2;                      // which chunk parity this warp handles
     constexpr int kChunkStep = 32 * (L::kEpiWarps / 4);
     uint8_t* stg_ptr = base_ptr + L::kTileBytes + ew * 4096;  // 1024-byte aligned (SWIZZLE_128B)
@@ -354,6 +407,13 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1) k_gemm_tc(const __gr
           constexpr float kX = H2 ? kLoUnscale : 1.0f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]) * (kNumAcc == 2 ? kX : 1.0f);
+          if constexpr (kNumAcc == 3) {
+            // two hi*hi accumulators (summed above, unscaled) + the cross terms
+            tmem_ld_32x32b_x32(acc0 + (uint32_t)(2 * BLOCK_N + c0), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]) * kX;
+          }
           if constexpr (kNumAcc == 4) {
             tmem_ld_32x32b_x32(acc0 + (uint32_t)(2 * BLOCK_N + c0), r);
             tmem_ld_32x32b_x32(acc0 + (uint32_t)(3 * BLOCK_N + c0), r2);
@@ -593,20 +653,20 @@ bool gemm_h2() {
   return h2;
 }
 
-template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2>
+template <int BLOCK_N, int NUM_HI, int STAGES, int ACC_BUFS, bool H2, bool AT = false>
 int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& ma2, int kb_split, const CUtensorMap& mbh, const CUtensorMap& mbl, const CUtensorMap& mc,
                        const CUtensorMap& mo2, float* C, int64_t M, int N, int K, int ldc, const Epilogue& ep, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>;
+  using L = SmemLayout<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT>;
   static PerDeviceOnce once;  // (the attribute is per device: a second GPU in the same process needs its own call)
   const int rc_cfg = once.run([]() -> int {
-    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    KP_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     return KPREG_OK;
   });
   if (rc_cfg) return rc_cfg;
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2><<<grid, gemm_threads(BLOCK_N), L::kTotal, stream>>>(ma, ma2, kb_split, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
+  k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT><<<grid, gemm_threads(BLOCK_N, AT), L::kTotal, stream>>>(ma, ma2, kb_split, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
@@ -718,6 +778,18 @@ int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int ld
   if (rc) return rc;
   Epilogue ep{row_scale, col_scale, col_shift, residual, ld_res, act, slope, out2, addend, ld2, ld_add, vec_ok, tma_store,
               post_res, ld_post, post_act};
+  // Long reductions with 64 / 128-column tiles: the split A operand goes through tensor memory (the mainloop is bound by
+  // shared-memory bandwidth: A's hi / lo boxes cost 16 KB of writes and 24 KB of MMA reads per k-block).  TMEM then holds the
+  // accumulators + 4 x 32 columns of A, so long K rotates hi*hi over two accumulators instead of three.
+  static const bool no_at = [] { const char* e = getenv("KPREG_GEMM_NO_AT"); return e && e[0] == '1'; }();
+  if (h2 && !no_at && kd >= 512 && block_n >= 64 && block_n <= 128) {
+    if (block_n == 64) {
+      if (num_hi == 3) return launch_tile_config<64, 3, 4, 1, true, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+      return launch_tile_config<64, 1, 4, 2, true, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    }
+    if (num_hi == 3) return launch_tile_config<128, 2, 4, 1, true, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+    return launch_tile_config<128, 1, 4, 1, true, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
+  }
   if (h2) {
     if (num_hi == 3) {
       if (block_n == 32) return launch_tile_config<32, 3, 4, 2, true>(ma, ma2, kb_split, mbh, mbl, mc, mo2, c, m, n, kd, ldc, ep, stream);
