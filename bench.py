@@ -62,7 +62,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.lines, self.proc, self.gpu = [], None, gpu_index
+        self.lines, self.proc, self.gpu, self.first = [], None, gpu_index, 0
 
     def start(self):
         try:
@@ -77,6 +77,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Forget the samples taken so far (ramp-up): only the timed region's clocks are reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -87,7 +91,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -546,6 +550,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), _lib.launch_count() - launches0, fam, last
 
+    # The clock sampler starts BEFORE the ramp-up: nvidia-smi's first query (NVML attaching to the GPU, ~0.6 s after the process
+    # starts) stalls kernel launches for ~0.1 s — seen as one 100-165 ms step at a fixed position of the timed region when the
+    # sampler was started right in front of it.  Its samples are only counted from the timed region on (ClockSampler.mark).
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KPREG_BENCH_NO_CLOCKS") else None
+    if sampler:
+        sampler.start()
     # clock / allocator / page-cache ramp-up of a fresh box: run the step untimed for ~2 s before the W warm-up steps
     t_ramp = time.perf_counter()
     ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
@@ -555,9 +565,8 @@ def main():
         path(b0.src_dev, b0.tgt_dev, b0.poses_dev, corr=b0.corr)
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KPREG_BENCH_NO_CLOCKS") else None
     if sampler:
-        sampler.start()
+        sampler.mark()
     ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True)
     steps_resident = timed.last_steps
     clocks = sampler.stop() if sampler else None
