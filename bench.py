@@ -57,14 +57,47 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  NVML is queried in-process
+    (pynvml) from a thread every KPREG_BENCH_CLOCK_MS (100) ms; `nvidia-smi -lms`, the fallback when pynvml is missing,
+    re-attaches on every poll and was seen to stall one step of the timed region by 50-110 ms."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event-reason bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.lines, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+        self.samples, self.stop_flag, self.thread, self.nvml, self.max_mhz = [], False, None, None, None
 
     def start(self):
+        period = float(os.environ.get("KPREG_BENCH_CLOCK_MS", "100")) / 1000.0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", os.environ.get("KPREG_BENCH_CLOCK_MS", "100")],
@@ -79,9 +112,17 @@ class ClockSampler:
 
     def mark(self):
         """Forget the samples taken so far (ramp-up): only the timed region's clocks are reported."""
-        self.first = len(self.lines)
+        self.first = len(self.samples) if self.nvml is not None else len(self.lines)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            got = self.samples[self.first:]
+            reasons = sorted(name for name, bit in self.BITS.items() if any(r & bit for _, r in got))
+            return {"sm_mhz": float(np.median([c for c, _ in got])) if got else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(got), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +145,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def kpconv_work(meta, cfg):
