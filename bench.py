@@ -551,6 +551,7 @@ def main():
         prof_steps = min(5, steps) if profile else 0
         if profile:
             per_step = sum(v[1] for v in _lib.profile_read().values()) // max(warmup, 1) + 8
+            prof_steps = max(1, min(prof_steps, 1800 // per_step))  # (a strong-scaling step is several sub-batches: fewer steps)
             _lib.profile_reserve(per_step * (prof_steps + 1))  # their events exist before the timed region starts
         # Long-lived Python objects (modules, cached packs, the batches) leave the collector's working set: a full
         # collection in the middle of a step otherwise stalls the launching thread for 0.1-0.2 s (seen as one 70-240 ms
