@@ -297,6 +297,33 @@ def test_encoder_fused_path_matches_reference_r2_fixture(golden_encoder_r2, pref
     assert err < TOL and max(errs) < TOL
 
 
+@pytest.mark.parametrize("variant", ["no_front", "no_front_no_pair", "no_front_no_chain"])
+def test_encoder_fallback_paths_match_reference_r2_fixture(golden_encoder_r2, variant, monkeypatch):
+    """The slower routes of the fused res2net unit — conv1 as its own GEMM + the mma.sync chain kernel (no front kernel), the
+    side-output chain scheme (no pair GEMM) and layer-by-layer chains at every width (no chain kernel) — against the same
+    reference fixture and bound as the default route: whichever route a shape or an environment switch selects, parity holds."""
+    from kpreg_b200 import kpconv_blocks as kb
+    from test_oracle import r2_case, r2_state_dict
+    g = golden_encoder_r2
+    cfg, d_bottle, clouds = r2_case(g, "tdm")
+    monkeypatch.setattr(kb, "FRONT_KERNEL", False)
+    if variant == "no_front_no_pair":
+        monkeypatch.setattr(ops, "linear_pair_supported", lambda *a, **k: False)
+    if variant == "no_front_no_chain":
+        monkeypatch.setattr(kb, "CHAIN_KERNEL", False)
+    np.random.seed(0)
+    enc = KPFEncoder(cfg, d_bottle)
+    enc.load_state_dict(r2_state_dict(g, "tdm", enc), strict=True)
+    enc = enc.cuda().eval()
+    meta = Preprocessor(cfg, index_dtype=torch.int32)([cuda(c) for c in clouds])
+    x0 = torch.ones((meta["points"][0].shape[0], 1), device="cuda")
+    with torch.no_grad():
+        y, skips = enc(x0, meta)
+    err = rel_err(y.cpu().numpy(), g["tdm_enc_out"])
+    record_parity(f"encoder_fallback[{variant}]_vs_reference_fixture", err, TOL)
+    assert err < TOL
+
+
 def test_row_positive_predicate_never_flips_on_encoder_features(oracle):
     """KPConv normalises by the number of neighbours whose feature SUM is positive (reference blocks :396-399, an fp32
     torch.sum).  The CUDA kernel decides the sign from an fp64 sum; the two can only differ for rows whose sum lies
