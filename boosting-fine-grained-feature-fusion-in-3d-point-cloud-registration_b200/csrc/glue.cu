@@ -61,6 +61,24 @@ __global__ void __launch_bounds__(256) k_linear_simple(const float* __restrict__
   }
 }
 
+// One launch in front of the statistics pass: cloud offsets (a serial prefix over a few hundred lengths) and the zeroed
+// fp64 moment buffers — instead of an offsets kernel plus one or two memsets per normalisation (25 normalisations per step).
+__global__ void __launch_bounds__(256) k_norm_prologue(const int32_t* __restrict__ lens, int n_clouds, int64_t* __restrict__ off,
+                                                       double* __restrict__ zero_a, double* __restrict__ zero_b, int64_t n_zero) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int c = 0; c < n_clouds; ++c) {
+      off[c] = acc;
+      acc += lens[c] > 0 ? lens[c] : 0;
+    }
+    off[n_clouds] = acc;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += (int64_t)gridDim.x * blockDim.x) {
+    zero_a[i] = 0.0;
+    if (zero_b) zero_b[i] = 0.0;
+  }
+}
+
 constexpr int kStatRows = 256;  // rows per CTA
 constexpr int kStatCh = 64;     // channels per CTA: 16 threads x float4; 16 row groups
 
@@ -343,9 +361,13 @@ extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t
   NormWs w = carve_norm(workspace, n_clouds, channels);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
   ProfScope prof(KPREG_FAM_NORM, stream);
-  int rc = launch_cloud_offsets(lens, n_clouds, w.off, stream);
-  if (rc) return rc;
-  KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
+  {
+    const int64_t n_zero = (int64_t)n_clouds * channels * 2;
+    int pb = ceil_div(n_zero, 256);
+    if (pb > 4 * kNumSMs) pb = 4 * kNumSMs;
+    k_norm_prologue<<<pb, 256, 0, stream>>>(lens, n_clouds, w.off, w.stats, nullptr, n_zero);
+    KP_LAUNCH_CHECK();
+  }
   dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
   if (channels <= 32) {
     dim3 grid_s((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
@@ -374,11 +396,14 @@ extern "C" int kpreg_segment_norm_backward(const float* x, int ldx, const float*
   NormWs w = carve_norm(workspace, n_clouds, channels);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
   ProfScope prof(KPREG_FAM_NORM, stream);
-  int rc = launch_cloud_offsets(lens, n_clouds, w.off, stream);
-  if (rc) return rc;
   // the forward statistics are recomputed from x (one extra pass; nothing is kept alive between forward and backward)
-  KP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
-  KP_CUDA_TRY(cudaMemsetAsync(w.bstats, 0, sizeof(double) * (size_t)n_clouds * channels * 2, stream));
+  {
+    const int64_t n_zero = (int64_t)n_clouds * channels * 2;
+    int pb = ceil_div(n_zero, 256);
+    if (pb > 4 * kNumSMs) pb = 4 * kNumSMs;
+    k_norm_prologue<<<pb, 256, 0, stream>>>(lens, n_clouds, w.off, w.stats, w.bstats, n_zero);
+    KP_LAUNCH_CHECK();
+  }
   dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
   if (channels <= 32) {
     dim3 grid_s((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
