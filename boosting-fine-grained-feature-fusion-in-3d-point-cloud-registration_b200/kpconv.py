@@ -67,6 +67,17 @@ class Preprocessor(nn.Module):
 
     @torch.no_grad()
     def forward(self, pts: List[torch.Tensor]):
+        out = None
+        for out in self.stages(pts, staged=False):
+            pass
+        return out
+
+    def stages(self, pts: List[torch.Tensor], staged: bool = True):
+        """The pyramid as a generator.  ``staged``: first yields the finest level alone — ``{'points': [p0], 'neighbors': [n0],
+        'stack_lengths': [l0], 'orders': [o0]}``, everything the encoder blocks in front of the first strided block read — and
+        then the complete dict.  A caller can enqueue those blocks and resume the generator under another CUDA stream
+        (``pipeline.RegistrationPath``): the radius queries of the coarser levels are instruction-bound and leave HBM idle,
+        the finest level's Linear / norm layers are the opposite.  ``forward`` is ``stages(pts, staged=False)`` run to its end."""
         cfg = self.cfg
         limits = cfg.neighborhood_limits
         arch = list(cfg.architecture)
@@ -100,6 +111,7 @@ class Preprocessor(nn.Module):
         r_normal = cfg.first_subsampling_dl * cfg.conv_radius
         level_points, level_lens, level_orders = [], [], []
         conv_tabs, pool_tabs, up_tabs = [], [], []
+        first_table = [None]  # staged: the finest level's conv table, finished ahead of the others
         layer_blocks, layer = [], 0
         grid = None           # cell grid of the current level (built one level ahead, see below)
         pending_up = None     # (fine points, fine lens, radius, limit, fine order): answered by the next level's grid
@@ -133,6 +145,13 @@ class Preprocessor(nn.Module):
             level_points.append(points)
             level_lens.append(lens)
             level_orders.append(order)
+            if staged and layer == 0 and conv_tabs[0] is not None and in_device.type == "cuda":
+                # the finest level is complete: its table's width is read back now (one small extra read-back)
+                st0 = stats[conv_tabs[0].slot].cpu()
+                if int(st0[1]) != 0:
+                    raise RuntimeError("Preprocessor: cell grid too large to index")
+                first_table[0] = self._finish(conv_tabs[0], int(st0[0]), dev)
+                yield {'points': [points], 'neighbors': [first_table[0]], 'stack_lengths': [lens], 'orders': [order]}
             if strided:
                 dl = 2 * r_normal / cfg.conv_radius
                 sub, counts = ops.subsample(points, lens, dl)
@@ -166,17 +185,13 @@ class Preprocessor(nn.Module):
         host_stats = stats.cpu()
         if int(host_stats[:, 1].max()) != 0:
             raise RuntimeError("Preprocessor: cell grid too large to index")
-        idx64 = self.index_dtype == torch.int64
 
         def finish(tab):
             if tab is None:
                 return torch.zeros((0, 1), dtype=torch.int64, device=dev)
-            width = min(int(host_stats[tab.slot, 0]), tab.limit)
-            if tab.rows.shape[0] < 1 or width < 1:
-                raise RuntimeError("Error")  # empty result: cpp_neighbors/wrapper.cpp:201-205
-            if width == tab.limit and not idx64:
-                return tab.rows
-            return ops.pack_rows(tab.rows, width, idx64)
+            if first_table[0] is not None and tab is conv_tabs[0]:
+                return first_table[0]
+            return self._finish(tab, int(host_stats[tab.slot, 0]), dev)
 
         n_levels = len(level_points)
         up_tabs += [None] * (n_levels - len(up_tabs))
@@ -188,11 +203,22 @@ class Preprocessor(nn.Module):
             'stack_lengths': level_lens,
         }
         if in_device.type != "cuda":
-            return {k: [t.to(in_device) for t in v] for k, v in data.items()}
+            yield {k: [t.to(in_device) for t in v] for k, v in data.items()}
+            return
         # extra key (not in the reference's dict): per level, the cell-sorted permutation of its rows — the blocks
         # hand it to the CUDA kernels as a processing order; consumers that do not know the key are unaffected
         data['orders'] = level_orders
-        return data
+        yield data
+
+    def _finish(self, tab, max_count, dev):
+        """An over-allocated [Nq, limit] table packed to its row width min(max_count, limit) and index dtype."""
+        idx64 = self.index_dtype == torch.int64
+        width = min(max_count, tab.limit)
+        if tab.rows.shape[0] < 1 or width < 1:
+            raise RuntimeError("Error")  # empty result: cpp_neighbors/wrapper.cpp:201-205
+        if width == tab.limit and not idx64:
+            return tab.rows
+        return ops.pack_rows(tab.rows, width, idx64)
 
 
 # The shipped model imports ``PreprocessorGPU`` (models/finegrained_regtr.py:32); this implementation is on the device
@@ -290,9 +316,19 @@ class KPFEncoder(torch.nn.Module):
             self.encoder_skip_dims.append(in_dim)
 
     def forward(self, x, batch):
-        skip_x = []
-        for block_i, block_op in enumerate(self.encoder_blocks):
+        return self.forward_blocks(x, batch, 0, len(self.encoder_blocks), [])
+
+    def first_strided_block(self) -> int:
+        """Index of the first block that reads anything beyond the finest level (its pool table, the next level's points)."""
+        for i in self.encoder_skips:
+            return i
+        return len(self.encoder_blocks)
+
+    def forward_blocks(self, x, batch, start: int, stop: int, skip_x):
+        """Blocks [start, stop) of ``forward`` — the finest level's blocks can run while the rest of the pyramid is still
+        being built (``Preprocessor.stages``).  ``skip_x`` collects the skip features across calls."""
+        for block_i in range(start, stop):
             if block_i in self.encoder_skips:
                 skip_x.append(x)
-            x = block_op(x, batch)
+            x = self.encoder_blocks[block_i](x, batch)
         return x, skip_x

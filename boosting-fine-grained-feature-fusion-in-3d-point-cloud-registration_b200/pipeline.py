@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -121,12 +123,51 @@ def synthetic_correspondences_batched(coarse_pts: torch.Tensor, coarse_lens: tor
 class RegistrationPath(torch.nn.Module):
     """Preprocessor + KPFEncoder + batched Kabsch behind one call."""
 
-    def __init__(self, cfg, index_dtype: torch.dtype = torch.int32, weights_threshold: Optional[float] = None):
+    def __init__(self, cfg, index_dtype: torch.dtype = torch.int32, weights_threshold: Optional[float] = None,
+                 overlap: Optional[bool] = None):
         super().__init__()
         self.cfg = cfg
         self.preprocessor = Preprocessor(cfg, index_dtype=index_dtype)
         self.kpf_encoder = KPFEncoder(cfg, cfg.d_embed)
         self.weights_threshold = weights_threshold
+        # overlap (off by default; KPREG_OVERLAP=1 or overlap=True): build the pyramid below the finest level on a second CUDA
+        # stream while the encoder's finest-level blocks run.  Results are identical — only the launch order across streams
+        # changes — and so, measured on B200, is the step time (53.5-54 ms either way at 64 pairs): every kernel of the step
+        # is launched wide enough to fill all SMs, so the two streams take turns instead of sharing them.
+        self.overlap = (os.environ.get("KPREG_OVERLAP", "")[:1] == "1") if overlap is None else bool(overlap)
+        self._side = {}
+
+    def _pyramid_and_encoder(self, clouds):
+        """(meta, encoder output).  Overlapped form: the radius queries / subsampling of the coarser levels are bound by
+        instruction issue and touch almost no HBM, the finest level's Linear / norm layers are bound by HBM — so after the
+        finest level's conv table the rest of the pyramid is issued on a side stream, behind the (already enqueued)
+        finest-level encoder blocks of the main stream.  Stream safety: the side stream first waits for everything the main
+        stream has been given (its inputs; tensors of earlier steps last read there), the main stream waits for the side
+        stream before the first strided block, and no main-stream allocation happens while the side stream is being fed."""
+        enc, pre = self.kpf_encoder, self.preprocessor
+        dev = clouds[0].device
+        first = enc.first_strided_block()
+        if not (self.overlap and dev.type == "cuda" and 0 < first < len(enc.encoder_blocks)):
+            meta = pre(clouds)
+            feats0 = torch.ones((meta['points'][0].shape[0], 1), dtype=torch.float32, device=meta['points'][0].device)
+            feats, _ = enc(feats0, meta)
+            return meta, feats
+        main = torch.cuda.current_stream(dev)
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(device=dev)
+        stages = pre.stages(clouds, staged=True)
+        meta0 = next(stages)
+        feats0 = torch.ones((meta0['points'][0].shape[0], 1), dtype=torch.float32, device=dev)
+        x, skips = enc.forward_blocks(feats0, meta0, 0, first, [])
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            meta = next(stages)
+            for _ in stages:  # run the generator to its end
+                pass
+        main.wait_stream(side)
+        feats, _ = enc.forward_blocks(x, meta, first, len(enc.encoder_blocks), skips)
+        return meta, feats
 
     @torch.no_grad()
     def forward(self, src_xyz: Sequence[torch.Tensor], tgt_xyz: Sequence[torch.Tensor], poses_gt: torch.Tensor,
@@ -137,9 +178,7 @@ class RegistrationPath(torch.nn.Module):
         by the caller (in the model they are the decoder's output; building the synthetic stand-ins is not part of the
         path).  Returns the encoder features, the per-layer poses [6,B,3,4] and the final-layer pose errors."""
         n_pairs = len(src_xyz)
-        meta = self.preprocessor(list(src_xyz) + list(tgt_xyz))
-        feats0 = torch.ones((meta['points'][0].shape[0], 1), dtype=torch.float32, device=meta['points'][0].device)
-        feats, _ = self.kpf_encoder(feats0, meta)
+        meta, feats = self._pyramid_and_encoder(list(src_xyz) + list(tgt_xyz))
         coarse = meta['points'][-1]
         poses_dev = poses_gt.to(coarse.device)
         if corr is not None:

@@ -229,3 +229,36 @@ def test_pyramid_architecture_ending_on_a_strided_block(oracle):
     assert_rows_equal_up_to_ties(meta["neighbors"][0], want["neighbors"][0], tie_rows(oracle, p, p, l, l, r))
     assert_rows_equal_up_to_ties(meta["pools"][0], want["pools"][0], tie_rows(oracle, sub, p, sub_l, l, r))
     assert_rows_equal_up_to_ties(meta["upsamples"][0], want["upsamples"][0], tie_rows(oracle, p, sub, l, sub_l, 2 * r))
+
+
+@pytest.mark.gpu
+def test_staged_pyramid_and_overlapped_path_match_the_plain_path():
+    """Preprocessor.stages (finest level first, the rest resumable under another CUDA stream) and RegistrationPath's
+    overlapped launch order return exactly what the one-shot path returns: same tables, same features, same poses."""
+    import torch
+    from kpreg_b200 import kpconv_config, synthetic
+    from kpreg_b200.kpconv import Preprocessor
+    from kpreg_b200.pipeline import RegistrationPath
+    cfg = kpconv_config("3dmatch")
+    dev = torch.device("cuda")
+    pairs = [synthetic.threedmatch_pair(seed=40 + i, n_raw=6000) for i in range(3)]
+    src = [torch.from_numpy(p[0]).to(dev) for p in pairs]
+    tgt = [torch.from_numpy(p[1]).to(dev) for p in pairs]
+    poses = torch.from_numpy(np.stack([p[2] for p in pairs])).to(dev)
+    pre = Preprocessor(cfg, index_dtype=torch.int32)
+    whole = pre(src + tgt)
+    staged = list(pre.stages(src + tgt, staged=True))
+    assert len(staged) == 2 and set(staged[0]) == {"points", "neighbors", "stack_lengths", "orders"}
+    assert torch.equal(staged[0]["neighbors"][0], whole["neighbors"][0]) and torch.equal(staged[0]["points"][0], whole["points"][0])
+    for key in ("points", "neighbors", "pools", "upsamples", "stack_lengths"):
+        assert all(torch.equal(a, b) for a, b in zip(staged[1][key], whole[key])), key
+    torch.manual_seed(0)
+    np.random.seed(0)
+    plain = RegistrationPath(cfg, index_dtype=torch.int32, weights_threshold=0.85, overlap=False).eval().to(dev)
+    both = RegistrationPath(cfg, index_dtype=torch.int32, weights_threshold=0.85, overlap=True).eval().to(dev)
+    both.load_state_dict(plain.state_dict())
+    a = plain(src, tgt, poses)
+    for _ in range(3):  # repeated steps: tensors of the previous step die while both streams are busy
+        b = both(src, tgt, poses)
+        torch.cuda.synchronize()
+        assert torch.equal(a["feats"], b["feats"]) and torch.equal(a["poses"], b["poses"])
