@@ -57,20 +57,20 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  NVML is queried in-process
-    (pynvml) from a thread every KPREG_BENCH_CLOCK_MS (100) ms; `nvidia-smi -lms`, the fallback when pynvml is missing,
-    re-attaches on every poll and was seen to stall one step of the timed region by 50-110 ms."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), read through NVML (pynvml) by
+    the launching thread itself right after the LAST timed step has been enqueued, while the GPU is still executing it.
+    Every earlier placement cost one step of the region 50-230 ms: a background `nvidia-smi -lms` or NVML thread stalled CUDA
+    calls directly, and even a synchronous query between two steps was followed, three steps later and at that position
+    every time, by one slow step (no such step without the queries: the driver appears to do deferred work after an NVML
+    clock query).  Fallback without pynvml: one `nvidia-smi` query at the same point."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    # NVML clocks-event-reason bits
-    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}  # NVML reason bits
 
     def __init__(self, gpu_index):
-        self.lines, self.proc, self.gpu, self.first = [], None, gpu_index, 0
-        self.samples, self.stop_flag, self.thread, self.nvml, self.max_mhz = [], False, None, None, None
+        self.gpu, self.samples, self.nvml, self.handle, self.max_mhz, self.calls = gpu_index, [], None, None, None, 0
 
     def start(self):
-        period = float(os.environ.get("KPREG_BENCH_CLOCK_MS", "100")) / 1000.0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -80,72 +80,44 @@ class ClockSampler:
                 ids = [v.strip() for v in vis.split(",") if v.strip()]
                 if self.gpu < len(ids) and ids[self.gpu].isdigit():
                     idx = int(ids[self.gpu])
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
-
-            def loop():
-                while not self.stop_flag:
-                    try:
-                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
-                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
-                    except Exception:
-                        pass
-                    time.sleep(period)
-
-            self.thread = threading.Thread(target=loop, daemon=True)
-            self.thread.start()
-            return
+            self.sample()  # the first query attaches NVML to the GPU: keep that out of the timed region as well
+            self.samples.clear()
         except Exception:
             self.nvml = None
+
+    def sample(self):
+        self.calls += 1
+        if self.nvml is not None:
+            try:
+                self.samples.append((float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)),
+                                     int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))))
+            except Exception:
+                pass
+            return
+        if self.calls != 1:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("KPREG_BENCH_CLOCK_MS", "100")],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            bits = 0
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    bits |= self.BITS[name]
+            self.samples.append((float(f[1]), bits))
+            self.max_mhz = float(f[2])
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def mark(self):
-        """Forget the samples taken so far (ramp-up): only the timed region's clocks are reported."""
-        self.first = len(self.samples) if self.nvml is not None else len(self.lines)
+            pass
 
     def stop(self):
-        if self.nvml is not None:
-            self.stop_flag = True
-            if self.thread is not None:
-                self.thread.join(timeout=2)
-            got = self.samples[self.first:]
-            reasons = sorted(name for name, bit in self.BITS.items() if any(r & bit for _, r in got))
-            return {"sm_mhz": float(np.median([c for c, _ in got])) if got else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                    "samples": len(got), "source": "nvml"}
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=10)  # its NVML teardown stalls CUDA calls of every process for ~0.2 s: keep it out of the next region
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines[self.first:]:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+        got = self.samples
+        reasons = sorted(name for name, bit in self.BITS.items() if any(r & bit for _, r in got))
+        return {"sm_mhz": float(np.median([c for c, _ in got])) if got else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(got), "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "when": "after the last timed step was enqueued, GPU still executing it"}
 
 
 def kpconv_work(meta, cfg):
@@ -441,6 +413,13 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # NVML is attached (and queried once) FIRST, seconds before anything is timed: the driver does some deferred work ~2.5 s
+    # after a process attaches — with the sampler started in front of the ramp-up that was one 60-230 ms step at a fixed
+    # position (the fourth) of the timed region in every second run.  The samples themselves are taken at the end of the region.
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KPREG_BENCH_NO_CLOCKS") else None
+    if sampler:
+        sampler.start()
+
     import torch.distributed as dist
     import kpreg_b200  # noqa: F401
     from kpreg_b200 import _lib, kpconv_blocks, kpconv_config
@@ -539,7 +518,7 @@ def main():
         host_table[0].copy_(table, non_blocking=True)
         return host_table[0], out
 
-    def timed(fn, steps, warmup, profile):
+    def timed(fn, steps, warmup, profile, between=None):
         if profile:
             _lib.profile(True)
         for _ in range(warmup):
@@ -552,6 +531,8 @@ def main():
         if profile:
             per_step = sum(v[1] for v in _lib.profile_read().values()) // max(warmup, 1) + 8
             prof_steps = max(1, min(prof_steps, 1800 // per_step))  # (a strong-scaling step is several sub-batches: fewer steps)
+            if os.environ.get("KPREG_BENCH_PROF_STEPS"):
+                prof_steps = max(1, min(steps, int(os.environ["KPREG_BENCH_PROF_STEPS"])))
             _lib.profile_reserve(per_step * (prof_steps + 1))  # their events exist before the timed region starts
         # Long-lived Python objects (modules, cached packs, the batches) leave the collector's working set: a full
         # collection in the middle of a step otherwise stalls the launching thread for 0.1-0.2 s (seen as one 70-240 ms
@@ -575,6 +556,12 @@ def main():
             last = fn()
             ends[i].record()
             flush.fill_(i & 1)  # evict L2 between timed steps (outside the events)
+            if between is not None and i == steps - 1:
+                # clock samples while the GPU is still busy with the last timed step's tail (about half a step is enqueued
+                # but not executed at this point) — see ClockSampler for why not earlier
+                for _ in range(5):
+                    between()
+                    time.sleep(0.003)
         torch.cuda.synchronize()
         gc.enable()
         if world > 1:
@@ -592,12 +579,6 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), _lib.launch_count() - launches0, fam, last
 
-    # The clock sampler starts BEFORE the ramp-up: nvidia-smi's first query (NVML attaching to the GPU, ~0.6 s after the process
-    # starts) stalls kernel launches for ~0.1 s — seen as one 100-165 ms step at a fixed position of the timed region when the
-    # sampler was started right in front of it.  Its samples are only counted from the timed region on (ClockSampler.mark).
-    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KPREG_BENCH_NO_CLOCKS") else None
-    if sampler:
-        sampler.start()
     # clock / allocator / page-cache ramp-up of a fresh box: run the step untimed for ~2 s before the W warm-up steps
     t_ramp = time.perf_counter()
     ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
@@ -607,9 +588,8 @@ def main():
         path(b0.src_dev, b0.tgt_dev, b0.poses_dev, corr=b0.corr)
         torch.cuda.synchronize()
 
-    if sampler:
-        sampler.mark()
-    ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True)
+    ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True,
+                                          between=sampler.sample if sampler else None)
     steps_resident = timed.last_steps
     clocks = sampler.stop() if sampler else None
     ms_e2e, _, _, last_e2e = timed(step_e2e, args.steps, args.warmup, profile=False)
