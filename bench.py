@@ -32,6 +32,13 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# Caching-allocator policy for a steady step time (measured, gpurun_out r3b/r3c): with the default policy the multi-GB
+# intermediates of a step are carved out of — and split — whatever large block is free, the free list drifts from step to
+# step, and every few dozen steps a 2.7 GB request finds no block: one cudaMalloc in the timed region (3-5 ms of host time
+# normally, 30-190 ms in one run of three — the "slow fourth step" of earlier rounds).  Blocks above 128 MB are therefore
+# never split: each large size keeps its own blocks and the steady state is reached in the first warm-up steps.
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "max_split_size_mb:128")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -521,8 +528,9 @@ def main():
     def timed(fn, steps, warmup, profile, between=None):
         if profile:
             _lib.profile(True)
+        last = None
         for _ in range(warmup):
-            fn()
+            last = fn()  # (kept while the next step runs, exactly as in the timed loop: the caching allocator sees one pattern)
             flush.fill_(1)
         torch.cuda.synchronize()
         # The per-family CUDA events are recorded in the first `prof_steps` steps of the timed region only: thousands of
@@ -548,12 +556,15 @@ def main():
             _lib.profile(True)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        last = None
+        host_ms = []
+        mem0 = torch.cuda.memory_stats(dev)
         for i in range(steps):
             if profile and i == prof_steps:
                 _lib.profile(False)  # stops recording; the records stay readable
             starts[i].record()
+            t_h = time.perf_counter()
             last = fn()
+            host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
             ends[i].record()
             flush.fill_(i & 1)  # evict L2 between timed steps (outside the events)
             if between is not None and i == steps - 1:
@@ -573,6 +584,11 @@ def main():
             fam = {k: (v[0] * steps / prof_steps, v[1] * steps / prof_steps) for k, v in fam.items()}  # scaled to `steps` steps
         per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
         timed.last_steps = [round(v, 2) for v in per_step_ms]
+        # diagnostics of the region (a slow step with a long host time is a host stall; cudaMalloc / cudaFree inside it is the allocator)
+        mem1 = torch.cuda.memory_stats(dev)
+        timed.last_host = host_ms
+        timed.last_alloc = {k: int(mem1.get(k, 0) - mem0.get(k, 0)) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries",
+                                                                              "reserved_bytes.all.current")}
         ms = sum(per_step_ms)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -582,18 +598,30 @@ def main():
     # clock / allocator / page-cache ramp-up of a fresh box: run the step untimed for ~2 s before the W warm-up steps
     t_ramp = time.perf_counter()
     ramp_s = 0.0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 2.0  # (profilers count launches: no time-based loop)
+    keep = out_r = None
     while time.perf_counter() - t_ramp < ramp_s:
-        # local work only: the iteration count is time-based and differs per rank, so NO collective in here
-        b0 = batches[0]
-        path(b0.src_dev, b0.tgt_dev, b0.poses_dev, corr=b0.corr)
+        # local work only: the iteration count is time-based and differs per rank, so NO collective in here.  The previous
+        # step's result stays alive while the next one runs, as in the timed loop: measured, the caching allocator otherwise
+        # meets a new live-set pattern in the timed region and called cudaMalloc in its fourth step in every run (3-5 ms of host
+        # time, and 30-170 ms in one run of five: the "slow fourth step").
+        for b in batches:
+            out_r = path(b.src_dev, b.tgt_dev, b.poses_dev, corr=b.corr)
+            keep = (result_rows(out_r), out_r)
+        flush.fill_(1)
         torch.cuda.synchronize()
+    del keep, out_r
 
     ms_total, launches, fam, last = timed(step_resident, args.steps, args.warmup, profile=True,
                                           between=sampler.sample if sampler else None)
-    steps_resident = timed.last_steps
+    steps_resident, host_resident, alloc_resident = timed.last_steps, timed.last_host, timed.last_alloc
     clocks = sampler.stop() if sampler else None
+    keep = None
+    for _ in range(0 if os.environ.get("KPREG_BENCH_NO_RAMP") else 4):  # the e2e step's own allocation pattern (H2D staging), untimed
+        keep = step_e2e()
+        flush.fill_(1)
+    del keep
     ms_e2e, _, _, last_e2e = timed(step_e2e, args.steps, args.warmup, profile=False)
-    steps_e2e = timed.last_steps
+    steps_e2e, host_e2e, alloc_e2e = timed.last_steps, timed.last_host, timed.last_alloc
 
     value = n_global * args.steps / (ms_total / 1000.0) if args.scaling == "strong" else n_local * world * args.steps / (ms_total / 1000.0)
     e2e_value = value * ms_total / ms_e2e
@@ -701,12 +729,14 @@ def main():
                        "kabsch_inputs": "decoder-shaped synthetic correspondences (the decoder is out of scope), built once from the batch's "
                                         "own coarse level outside the timed region and resident on the device",
                        "l2": "256 MiB write between timed steps (outside the CUDA events)",
-                       "ramp_up": "2 s of untimed steps before the W warm-up steps (fresh-box clocks / allocator)"},
+                       "allocator": "PYTORCH_CUDA_ALLOC_CONF=" + os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""),
+                       "ramp_up": "2 s of untimed steps before the W warm-up steps (fresh-box clocks / allocator), 4 untimed e2e steps before the e2e warm-up"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_copies_per_step": 2 * len(my_batches)},
             "gpu_launches": int(launches),
-            "step_ms": {"resident": steps_resident, "e2e": steps_e2e},
+            "step_ms": {"resident": steps_resident, "e2e": steps_e2e, "host_enqueue_resident": host_resident, "host_enqueue_e2e": host_e2e,
+                        "allocator_in_region": {"resident": alloc_resident, "e2e": alloc_e2e}},
             "roofline": roof,
             "cpu_baseline": cpu,
             "parity_check": parity,

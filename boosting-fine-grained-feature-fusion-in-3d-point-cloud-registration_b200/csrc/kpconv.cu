@@ -44,6 +44,21 @@ bool g_gather_mma = true;            // aggregate on mma.sync (3xTF32); false = 
 bool g_c1_by_neighbour = false;      // KPREG_C1_BY_NEIGHBOUR=1: the lane-per-neighbour c_in == 1 kernel also for 'sum' aggregation (A/B)
 bool g_no_c1 = false;                // KPREG_NO_C1=1: c_in == 1 goes through the generic gather + GEMM path (A/B measurements)
 bool g_gather_novec = false;         // KPREG_GATHER_NOVEC=1: scalar-load channel binding even for aligned rows (A/B measurements)
+// Measured (profiles/r3_sweep_gather_grid.txt, 64 pairs): 32 CTAs per SM leave a 5-6-wave grid whose last wave runs at falling
+// occupancy; 128 per SM with slices of >= 16 queries took the KPConv calls of a step from 20.15 to 19.63 ms, 256+ lose it again.
+int g_gather_ctas_per_sm = 128;      // KPREG_GATHER_CTAS_PER_SM: upper bound of the gather-style grids, in CTAs per SM
+int g_gather_min_slice = 16;         // KPREG_GATHER_MIN_SLICE: fewest queries a CTA's contiguous slice holds
+
+// Grid of the warp-per-query kernels (each CTA walks a contiguous slice of the processing order).
+int gather_blocks(int64_t n_q) {
+  // small query sets keep one query per warp (a single ModelNet pair must still spread over the SMs)
+  const int64_t fine = (n_q + kGatherWarps - 1) / kGatherWarps, sliced = (n_q + g_gather_min_slice - 1) / g_gather_min_slice;
+  const int64_t floor_blocks = (int64_t)kNumSMs * 32, cap = (int64_t)kNumSMs * g_gather_ctas_per_sm;
+  int64_t blocks = sliced > floor_blocks ? sliced : floor_blocks;
+  if (blocks > fine) blocks = fine;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
 
 __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ x, int64_t n_s, int c_in,
                                                       unsigned char* __restrict__ pos) {
@@ -857,9 +872,7 @@ template <typename IdxT>
 int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const float* x, const unsigned char* row_pos,
                   const float* kp, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence,
                   int aggregation, float* agg, float* inv_num, const int32_t* order, cudaStream_t stream) {
-  int blocks = ceil_div(n_q, kGatherWarps);
-  const int cap = kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
+  const int blocks = gather_blocks(n_q);
   const IdxT* ip = static_cast<const IdxT*>(idx);
   ProfScope prof(KPREG_FAM_GATHER, stream);
   if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && n_s < ((int64_t)1 << 31) && g_gather_mma) {
@@ -902,9 +915,7 @@ template <typename IdxT>
 int launch_scatter(const float* q_pts, const float* s_pts, const void* idx, const float* kp, const float* d_agg, int64_t n_q,
                    int64_t n_s, int n_nbrs, int n_kpts, int c_in, float extent, int influence, int aggregation, float* d_x,
                    const int32_t* order, cudaStream_t stream) {
-  int blocks = ceil_div(n_q, kGatherWarps);
-  const int cap = kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
+  const int blocks = gather_blocks(n_q);
   const IdxT* ip = static_cast<const IdxT*>(idx);
 #define KP_SCATTER(CPL)                                                                                                  \
   k_kpconv_scatter<IdxT, CPL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, kp, d_agg, n_q, n_s, n_nbrs,   \
@@ -942,6 +953,10 @@ struct GatherModeInit {
     if (e && e[0] == '1') kpreg::g_no_c1 = true;
     e = getenv("KPREG_C1_BY_NEIGHBOUR");
     if (e && e[0] == '1') kpreg::g_c1_by_neighbour = true;
+    e = getenv("KPREG_GATHER_CTAS_PER_SM");
+    if (e && atoi(e) > 0) kpreg::g_gather_ctas_per_sm = atoi(e);
+    e = getenv("KPREG_GATHER_MIN_SLICE");
+    if (e && atoi(e) > 0) kpreg::g_gather_min_slice = atoi(e);
   }
 } g_gather_mode_init;
 }  // namespace
@@ -966,8 +981,7 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   cudaStream_t stream = (cudaStream_t)stream_;
   if (c_in == 1 && c_out <= 128 && n_nbrs <= 64 && gemm != 2 && n_s > 0 && !g_no_c1) {
     // single input channel: gather, contraction and normalisation in one kernel (raw [K, 1, c_out] weights)
-    int blocks = ceil_div(n_q, kGatherWarps);
-    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+    const int blocks = gather_blocks(n_q);
     ProfScope prof(KPREG_FAM_GATHER, stream);
 #define KP_C1_(IdxT, CPL, INFL)                                                                                                       \
   k_kpconv_c1<IdxT, CPL, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, static_cast<const IdxT*>(idx), x,               \
