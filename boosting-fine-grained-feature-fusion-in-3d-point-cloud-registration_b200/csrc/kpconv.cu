@@ -48,6 +48,7 @@ bool g_gather_novec = false;         // KPREG_GATHER_NOVEC=1: scalar-load channe
 // occupancy; 128 per SM with slices of >= 16 queries took the KPConv calls of a step from 20.15 to 19.63 ms, 256+ lose it again.
 int g_gather_ctas_per_sm = 128;      // KPREG_GATHER_CTAS_PER_SM: upper bound of the gather-style grids, in CTAs per SM
 int g_gather_min_slice = 16;         // KPREG_GATHER_MIN_SLICE: fewest queries a CTA's contiguous slice holds
+bool g_gather_groups = true;         // KPREG_GATHER_GROUPS=0: rows wider than 64 channels stay on one warp per query (A/B measurements)
 
 // Grid of the warp-per-query kernels (each CTA walks a contiguous slice of the processing order).
 int gather_blocks(int64_t n_q) {
@@ -258,12 +259,16 @@ __device__ __forceinline__ float influence_one(float rx, float ry, float rz, flo
 // resident CTAs per SM the register allocation must leave room for (the occupancies the kernel was tuned at)
 constexpr int gather_min_blocks(int nt) { return nt <= 4 ? 6 : (nt <= 8 ? 5 : (nt <= 16 ? 3 : 2)); }
 
-template <typename IdxT, int NT, bool VEC, int INFL>  // NT = number of 8-channel tiles (c_in <= 8 * NT)
+// GRP (wide rows, c_in > 8 * NT): the work item is (query, channel group of 8 * NT channels) instead of the query, consecutive
+// items = the groups of one query, so the warps of a CTA share the query's index row and neighbour coordinates through L1 and
+// each recomputes the influences.  One warp holding all of a 128- / 256-channel row needs 64 / 128 accumulator registers
+// (3 / 2 CTAs per SM, and the kernel is latency-bound): measured per query and SM, 2 000 / 5 800 cycles against 719 at 64 channels.
+template <typename IdxT, int NT, bool VEC, int INFL, bool GRP = false>  // NT = number of 8-channel tiles (c_in <= 8 * NT unless GRP)
 __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kpconv_gather_mma(
     const float* __restrict__ q_pts, const float* __restrict__ s_pts, const IdxT* __restrict__ idx, const float* __restrict__ x,
     const unsigned char* __restrict__ row_pos, const float* __restrict__ kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
     int n_kpts, int c_in, float extent, int influence, int aggregation, float* __restrict__ agg, float* __restrict__ inv_num,
-    const int32_t* __restrict__ order) {
+    const int32_t* __restrict__ order, int n_groups) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const float inv_extent = 1.0f / extent;
@@ -277,32 +282,41 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
 
   // each CTA owns a CONTIGUOUS slice of the (spatially sorted) processing order, so the neighbourhoods its warps
   // gather overlap and stay in this SM's L1
-  const int64_t per_cta = (n_q + gridDim.x - 1) / gridDim.x;
-  const int64_t it_end = min(n_q, (int64_t)(blockIdx.x + 1) * per_cta);
+  const int64_t n_items = GRP ? n_q * n_groups : n_q;
+  const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+  const int64_t it_end = min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
   int64_t it = (int64_t)blockIdx.x * per_cta + warp;
   // index rows (neighbours h = lane and h = lane + 32) are fetched TWO queries ahead: one query ahead their values are in
   // registers, and the support points / feature rows they name are requested into L1 while the current query is processed
   // (the gather is latency-bound: L1 hit rate 78 % without this)
   int64_t n_nx = 0, n_n2 = 0;
+  int grp_nx = 0, grp_n2 = 0;  // (GRP) channel group of the item
   IdxT raw_nx[2] = {(IdxT)n_s32, (IdxT)n_s32}, raw_n2[2] = {(IdxT)n_s32, (IdxT)n_s32};
-  auto load_row = [&](int64_t i, int64_t& nn, IdxT (&rw)[2]) {
+  auto load_row = [&](int64_t i, int64_t& nn, int& gg, IdxT (&rw)[2]) {
     rw[0] = rw[1] = (IdxT)n_s32;
     if (i < it_end) {
-      nn = order ? (int64_t)order[i] : i;  // processing order only, never the result
+      int64_t q = i;
+      if constexpr (GRP) {
+        q = i / n_groups;
+        gg = (int)(i - q * n_groups);
+      }
+      nn = order ? (int64_t)order[q] : q;  // processing order only, never the result
 #pragma unroll
       for (int r = 0; r < 2; ++r)
         if (lane + 32 * r < n_nbrs) rw[r] = idx[nn * n_nbrs + lane + 32 * r];
     }
   };
-  load_row(it, n_nx, raw_nx);
-  load_row(it + kGatherWarps, n_n2, raw_n2);
+  load_row(it, n_nx, grp_nx, raw_nx);
+  load_row(it + kGatherWarps, n_n2, grp_n2, raw_n2);
   for (; it < it_end; it += kGatherWarps) {
     const int64_t n = n_nx;
+    const int c_off = GRP ? grp_nx * 8 * NT : 0;  // first channel of this item's group
     const IdxT raw[2] = {raw_nx[0], raw_nx[1]};
     n_nx = n_n2;
+    grp_nx = grp_n2;
     raw_nx[0] = raw_n2[0];
     raw_nx[1] = raw_n2[1];
-    load_row(it + 2 * kGatherWarps, n_n2, raw_n2);
+    load_row(it + 2 * kGatherWarps, n_n2, grp_n2, raw_n2);
 #if KPREG_GATHER_PREFETCH
     // (measured: -3 % at c_in = 32, +3-5 % at c_in >= 64 — rows of several cache lines — so narrow rows only)
     if (NT <= 4 && it + kGatherWarps < it_end) {
@@ -394,8 +408,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
       if (!__any_sync(0xffffffffu, va || vb)) continue;  // eight shadow neighbours: nothing to add
       float a_hi[4], a_lo[4];
       step_influences(h0, va, vb, a_hi, a_lo);
-      const float* __restrict__ xa = x + (int64_t)(va ? ja : 0) * c_in;
-      const float* __restrict__ xb = x + (int64_t)(vb ? jb : 0) * c_in;
+      const float* __restrict__ xa = x + (int64_t)(va ? ja : 0) * c_in + c_off;
+      const float* __restrict__ xb = x + (int64_t)(vb ? jb : 0) * c_in + c_off;
       // (Measured: feeding the B operand pre-split — features split once per layer into interleaved (hi, lo) pairs instead of
       // once per gathering lane, 30 % fewer instructions — made the step's aggregate kernels 40 % SLOWER: the kernel is bound
       // by the gather path (L1 / L2 latency at a 78 % L1 hit rate), and pre-split rows are twice as long.)
@@ -404,8 +418,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
 #pragma unroll
         for (int m = 0; m < NT / 4; ++m) {
           const int c = NT * g + 4 * m;
-          fa[m] = (va && c < c_in) ? __ldg(reinterpret_cast<const float4*>(xa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          fb[m] = (vb && c < c_in) ? __ldg(reinterpret_cast<const float4*>(xb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          fa[m] = (va && c_off + c < c_in) ? __ldg(reinterpret_cast<const float4*>(xa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          fb[m] = (vb && c_off + c < c_in) ? __ldg(reinterpret_cast<const float4*>(xb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int m = 0; m < NT / 4; ++m)
@@ -415,48 +429,49 @@ __global__ void __launch_bounds__(kGatherWarps * 32, gather_min_blocks(NT)) k_kp
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
           const int c = 8 * i + g;
-          mma3(acc[i], a_hi, a_lo, (va && c < c_in) ? xa[c] : 0.f, (vb && c < c_in) ? xb[c] : 0.f);
+          mma3(acc[i], a_hi, a_lo, (va && c_off + c < c_in) ? xa[c] : 0.f, (vb && c_off + c < c_in) ? xb[c] : 0.f);
         }
       }
     }
     // D fragment: rows (kernel points) g and g + 8, columns (channels) 8 i + 2 t, + 1
-    float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in;
+    float* __restrict__ arow = agg + n * (int64_t)n_kpts * c_in + c_off;
+    const bool first_group = !GRP || c_off == 0;  // one item per query reports the neighbour count
     if constexpr (VEC) {
       // D fragment under the VEC binding: acc[i][0|2] <-> channel 2t * NT + i, acc[i][1|3] <-> channel (2t + 1) * NT + i
 #pragma unroll
       for (int m = 0; m < NT / 4; ++m) {
         const int ce = 2 * t * NT + 4 * m, co = (2 * t + 1) * NT + 4 * m;
-        if (ce < c_in) {
+        if (c_off + ce < c_in) {
           if (k0_ok) *reinterpret_cast<float4*>(arow + g * c_in + ce) = make_float4(acc[4 * m][0], acc[4 * m + 1][0], acc[4 * m + 2][0], acc[4 * m + 3][0]);
           if (k1_ok) *reinterpret_cast<float4*>(arow + (g + 8) * c_in + ce) = make_float4(acc[4 * m][2], acc[4 * m + 1][2], acc[4 * m + 2][2], acc[4 * m + 3][2]);
         }
-        if (co < c_in) {
+        if (c_off + co < c_in) {
           if (k0_ok) *reinterpret_cast<float4*>(arow + g * c_in + co) = make_float4(acc[4 * m][1], acc[4 * m + 1][1], acc[4 * m + 2][1], acc[4 * m + 3][1]);
           if (k1_ok) *reinterpret_cast<float4*>(arow + (g + 8) * c_in + co) = make_float4(acc[4 * m][3], acc[4 * m + 1][3], acc[4 * m + 2][3], acc[4 * m + 3][3]);
         }
       }
-      if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+      if (lane == 0 && first_group) inv_num[n] = 1.0f / (float)max(num, 1);
       continue;
     }
     const bool pair_ok = (c_in & 1) == 0;  // (row * c_in + even column) is then 8-byte aligned: one float2 store
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int c = 8 * i + 2 * t;
-      if (pair_ok && c + 1 < c_in) {
+      if (pair_ok && c_off + c + 1 < c_in) {
         if (k0_ok) *reinterpret_cast<float2*>(arow + g * c_in + c) = make_float2(acc[i][0], acc[i][1]);
         if (k1_ok) *reinterpret_cast<float2*>(arow + (g + 8) * c_in + c) = make_float2(acc[i][2], acc[i][3]);
       } else {
         if (k0_ok) {
-          if (c < c_in) arow[g * c_in + c] = acc[i][0];
-          if (c + 1 < c_in) arow[g * c_in + c + 1] = acc[i][1];
+          if (c_off + c < c_in) arow[g * c_in + c] = acc[i][0];
+          if (c_off + c + 1 < c_in) arow[g * c_in + c + 1] = acc[i][1];
         }
         if (k1_ok) {
-          if (c < c_in) arow[(g + 8) * c_in + c] = acc[i][2];
-          if (c + 1 < c_in) arow[(g + 8) * c_in + c + 1] = acc[i][3];
+          if (c_off + c < c_in) arow[(g + 8) * c_in + c] = acc[i][2];
+          if (c_off + c + 1 < c_in) arow[(g + 8) * c_in + c + 1] = acc[i][3];
         }
       }
     }
-    if (lane == 0) inv_num[n] = 1.0f / (float)max(num, 1);
+    if (lane == 0 && first_group) inv_num[n] = 1.0f / (float)max(num, 1);
   }
 }
 
@@ -876,16 +891,29 @@ int launch_gather(const float* q_pts, const float* s_pts, const void* idx, const
   const IdxT* ip = static_cast<const IdxT*>(idx);
   ProfScope prof(KPREG_FAM_GATHER, stream);
   if (n_nbrs <= 64 && n_kpts <= 16 && c_in <= 256 && n_s < ((int64_t)1 << 31) && g_gather_mma) {
+    // float4 path: whole rows of x and of the aggregate are 16-byte aligned
+    const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
+    if (c_in > 64 && vec && g_gather_groups) {
+      // wide rows: (query, 64-channel group) work items on the 64-channel kernel (see GRP above)
+      const int n_groups = (c_in + 63) / 64;
+      const int gblocks = gather_blocks(n_q * n_groups);
+      if (influence == 1)
+        k_kpconv_gather_mma<IdxT, 8, true, 1, true><<<gblocks, kGatherWarps * 32, 0, stream>>>(
+            q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, n_kpts, c_in, extent, influence, aggregation, agg, inv_num, order, n_groups);
+      else
+        k_kpconv_gather_mma<IdxT, 8, true, -1, true><<<gblocks, kGatherWarps * 32, 0, stream>>>(
+            q_pts, s_pts, ip, x, row_pos, kp, n_q, n_s, n_nbrs, n_kpts, c_in, extent, influence, aggregation, agg, inv_num, order, n_groups);
+      KP_LAUNCH_CHECK();
+      return KPREG_OK;
+    }
 #define KP_GATHER_MMA_(NT, VEC, INFL)                                                                                          \
   k_kpconv_gather_mma<IdxT, NT, VEC, INFL><<<blocks, kGatherWarps * 32, 0, stream>>>(q_pts, s_pts, ip, x, row_pos, kp, n_q,    \
                                                                                      n_s, n_nbrs, n_kpts, c_in, extent,        \
-                                                                                     influence, aggregation, agg, inv_num, order)
+                                                                                     influence, aggregation, agg, inv_num, order, 1)
 #define KP_GATHER_MMA(NT, VEC)                                                \
   do {                                                                        \
     if (influence == 1) KP_GATHER_MMA_(NT, VEC, 1); else KP_GATHER_MMA_(NT, VEC, -1); \
   } while (0)
-    // float4 path: whole rows of x and of the aggregate are 16-byte aligned
-    const bool vec = (c_in % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(agg)) & 15) == 0 && !g_gather_novec;
     if (c_in <= 8) KP_GATHER_MMA(1, false);
     else if (c_in <= 16) KP_GATHER_MMA(2, false);
     else if (c_in <= 32) { if (vec) KP_GATHER_MMA(4, true); else KP_GATHER_MMA(4, false); }
@@ -955,6 +983,8 @@ struct GatherModeInit {
     if (e && e[0] == '1') kpreg::g_c1_by_neighbour = true;
     e = getenv("KPREG_GATHER_CTAS_PER_SM");
     if (e && atoi(e) > 0) kpreg::g_gather_ctas_per_sm = atoi(e);
+    e = getenv("KPREG_GATHER_GROUPS");
+    if (e && e[0] == '0') kpreg::g_gather_groups = false;
     e = getenv("KPREG_GATHER_MIN_SLICE");
     if (e && atoi(e) > 0) kpreg::g_gather_min_slice = atoi(e);
   }
