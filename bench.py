@@ -674,7 +674,8 @@ def main():
         roof["families"] = fams
         # DRAM traffic of the family from the committed ncu capture of this build (dram__bytes_read.sum + dram__bytes_write.sum
         # over one step's launches), scaled to this run's pairs per step
-        tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+        tpath = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r3_dram_traffic.json", "r2_dram_traffic.json")) if os.path.exists(q)),
+                     os.path.join(ROOT, "profiles", "r3_dram_traffic.json"))
         fam_kernels = {"linear": ("k_gemm_tc", "k_chain", "k_res2net_front"), "kpconv_contract": ("k_gemm_tc",),
                        "kpconv_gather": ("k_kpconv_gather_mma", "k_kpconv_c1"), "grid_query": ("k_grid_query",)}.get(top)
         if os.path.exists(tpath) and fam_kernels:
@@ -683,10 +684,10 @@ def main():
             if fs:
                 roof["traffic"] = sum(f["dram_read_MB"] + f["dram_write_MB"] for f in fs) * 1e6 * n_local / tr["pairs"]
                 roof["traffic_note"] = (f"bytes per step, all {' + '.join(fam_kernels)} launches (ncu capture at {tr['pairs']} pairs/step, "
-                                        f"profiles/r2_dram_traffic.json, scaled to {n_local}; k_gemm_tc also serves the KPConv contraction); "
+                                        f"profiles/{os.path.basename(tpath)}, scaled to {n_local}; k_gemm_tc also serves the KPConv contraction); "
                                         "achieved / algorithmic figures are per step as well")
         if roof["traffic"] is None:
-            roof["traffic_note"] = "profiles/r2_dram_traffic.json is missing"
+            roof["traffic_note"] = "profiles/r3_dram_traffic.json is missing"
         roof["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback"
         roof["per_step_ms"] = {k: round(v, 4) for k, v in fam_ms.items()}
         roof["launches_per_step"] = {k: v for k, v in fam_n.items()}
