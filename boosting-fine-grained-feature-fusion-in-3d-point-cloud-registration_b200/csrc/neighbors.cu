@@ -375,7 +375,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_grid_query(
 }
 
 // ---- hot path: one thread per query ------------------------------------------------------------------------------
-constexpr int kTqWarps = 4;       // warps (= 32-query blocks) per CTA: consecutive blocks share spans through L1
+// warps (= 32-query blocks) per CTA.  Measured at 64 pairs (radius queries of a step): 8 warps 8.7 ms, 4 warps 6.96, 2 warps 6.84,
+// 1 warp 6.80 — a CTA's slot is only refilled when its slowest warp is done, and that costs more than the L1 lines
+// consecutive blocks of one CTA share.
+constexpr int kTqWarps = 1;
 constexpr int kTqCap = 48;        // a lane buffers up to kTqCap - 1 hits; more -> exact_query_warp
 constexpr int kTqPitch = kTqCap + 1;  // odd pitch (in 4-byte entries): lane-own and row-cooperative accesses are both conflict-free
 constexpr int kTqMaxWidth = 47;   // row widths served by this kernel
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kTqWarps * 32, 32 / kTqWarps) k_grid_query_tq(
   int* const s_row_end = s_row_start + 32;
   const GridHeader h = *hdr;
 
-  // one 32-query block of the (cell-sorted) processing order per warp; a CTA's four blocks are consecutive (shared L1 lines)
+  // one 32-query block of the (cell-sorted) processing order per warp
   const int64_t blk = (int64_t)blockIdx.x * kTqWarps + warp;
   const int64_t it = (blk << 5) + lane;
   const bool valid = it < n_queries;
