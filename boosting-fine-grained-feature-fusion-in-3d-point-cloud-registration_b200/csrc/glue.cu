@@ -97,13 +97,14 @@ __device__ __forceinline__ void stat_flush(double* __restrict__ stats, int cloud
 // TX = threads per row (8 for rows of <= 32 channels: no idle lanes), 256 / TX row groups.
 template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_stats(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
-                                                       int n_clouds, int64_t n_rows, int channels, double* __restrict__ stats) {
+                                                       int n_clouds, int64_t n_rows, int channels, double* __restrict__ stats,
+                                                       int rows_per_cta = kStatRows) {
   constexpr int RY = 256 / TX, CH = 4 * TX;
   __shared__ double s_sum[RY][CH], s_sq[RY][CH];
   const int cx = threadIdx.x % TX, ry = threadIdx.x / TX;
   const int ch = blockIdx.y * CH + cx * 4;
-  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
-  const int64_t r1 = min(n_rows, r0 + kStatRows);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(n_rows, r0 + rows_per_cta);
   const int c_first = cloud_of(off, n_clouds, r0);
   const int c_last = cloud_of(off, n_clouds, r1 - 1);
   const bool live = ch < channels;  // channels is a multiple of 4
@@ -162,13 +163,13 @@ template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
                                                        int n_clouds, int64_t n_rows, int channels, const double* __restrict__ stats,
                                                        float eps, const float* __restrict__ residual, int ld_res, int act, float slope,
-                                                       float* __restrict__ out, int ldo) {
+                                                       float* __restrict__ out, int ldo, int rows_per_cta) {
   constexpr int RY = 256 / TX;
   const int cx = threadIdx.x % TX, ry = threadIdx.x / TX;
   const int ch = blockIdx.y * (4 * TX) + cx * 4;
   if (ch >= channels) return;  // channels is a multiple of 4
-  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
-  const int64_t r1 = min(n_rows, r0 + kStatRows);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(n_rows, r0 + rows_per_cta);
   int c = -1;
   int64_t c_end = 0;
   float mean[4], rstd[4];
@@ -368,20 +369,21 @@ extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t
     k_norm_prologue<<<pb, 256, 0, stream>>>(lens, n_clouds, w.off, w.stats, nullptr, n_zero);
     KP_LAUNCH_CHECK();
   }
-  dim3 grid((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, kStatCh));
-  if (channels <= 32) {
-    dim3 grid_s((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
-    k_segnorm_stats<8><<<grid_s, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
-  } else {
-    k_segnorm_stats<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats);
-  }
+  // rows per CTA: a 256-row chunk of a narrow tensor is 32-64 KB, which an SM streams in under a microsecond — the CTA's
+  // fixed work (two cloud searches, the shared-memory reduction, its atomics) then sets the rate; large row counts get longer chunks
+  static const int rows_env = [] { const char* e = getenv("KPREG_NORM_ROWS"); return e ? atoi(e) : 0; }();  // A/B measurements
+  int rows = kStatRows;
+  const int col_ctas = ceil_div(channels, channels <= 32 ? 32 : kStatCh);
+  while (rows < 2048 && ceil_div(n_rows, 2 * rows) * (int64_t)col_ctas >= (int64_t)kNumSMs * 16) rows *= 2;  // (profiles/r3_sweep_norm_rows.txt)
+  if (rows_env >= 256) rows = rows_env;
+  dim3 grid((unsigned)ceil_div(n_rows, rows), (unsigned)col_ctas);
+  if (channels <= 32) k_segnorm_stats<8><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, rows);
+  else k_segnorm_stats<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, rows);
   KP_LAUNCH_CHECK();
-  if (channels <= 32) {
-    dim3 grid_a((unsigned)ceil_div(n_rows, kStatRows), (unsigned)ceil_div(channels, 32));
-    k_segnorm_apply<8><<<grid_a, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo);
-  } else {
-    k_segnorm_apply<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo);
-  }
+  if (channels <= 32)
+    k_segnorm_apply<8><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows);
+  else
+    k_segnorm_apply<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }
