@@ -56,7 +56,7 @@ _SIGNATURES = {
     "kpreg_linear_backward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_int, _c_ptr, _c_ptr,
                                        _c_size, _c_ptr]),
     "kpreg_linear_pair_forward": (_c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_int, _c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_int,
-                                           _c_f32, _c_ptr, _c_int, _c_ptr]),
+                                           _c_f32, _c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_ptr]),
     "kpreg_segment_norm_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_segment_norm_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
                                             _c_f32, _c_ptr, _c_int, _c_ptr, _c_size, _c_ptr]),

@@ -333,8 +333,10 @@ extern "C" int kpreg_linear_forward(const float* x, int ldx, const float* weight
 
 extern "C" int kpreg_linear_pair_forward(const float* x1, int ld1, int k1, const float* x2, int ld2, int k2, const float* w_split,
                                          int64_t m_rows, int n_dim, const float* col_scale, const float* col_shift, int act,
-                                         float slope, float* out, int ldc, void* stream_) {
+                                         float slope, const float* post_residual, int ld_post, int post_act, float* out, int ldc,
+                                         void* stream_) {
   if (m_rows < 0 || k1 < 4 || k2 < 1 || n_dim < 8 || ld1 < k1 || ld2 < k2 || ldc < n_dim || act < 0 || act > 2) return KPREG_E_INVALID;
+  if (post_act < 0 || post_act > 2 || (post_residual && ld_post < n_dim)) return KPREG_E_INVALID;
   if (m_rows == 0) return KPREG_OK;
   if (!x1 || !x2 || !w_split || !out) return KPREG_E_INVALID;
   const int kd = (k1 + 31) / 32 * 32 + k2;
@@ -342,7 +344,7 @@ extern "C" int kpreg_linear_pair_forward(const float* x1, int ld1, int k1, const
   cudaStream_t stream = (cudaStream_t)stream_;
   ProfScope prof(KPREG_FAM_LINEAR, stream);
   return launch_gemm_tc_pair(x1, ld1, k1, x2, ld2, w_split, out, ldc, m_rows, kd, n_dim, nullptr, col_scale, col_shift, nullptr, 0, act,
-                             slope, nullptr, 0, nullptr, 0, nullptr, 0, 0, stream);
+                             slope, nullptr, 0, nullptr, 0, post_residual, ld_post, post_act, stream);
 }
 
 extern "C" int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, size_t* bytes) {

@@ -40,6 +40,7 @@ CHAIN_KERNEL = True
 import os as _os
 # (the front kernel always splits operands into fp16 pairs: under KPREG_GEMM_TF32=1 — fp32 range — it is not used)
 FRONT_KERNEL = _os.environ.get("KPREG_NO_FRONT", "")[:1] != "1" and _os.environ.get("KPREG_GEMM_TF32", "")[:1] != "1"
+PAIR_CONV3 = _os.environ.get("KPREG_NO_PAIR_CONV3", "")[:1] != "1"  # wide res2net units: conv3 + residual projection over (z, x) without copying x
 
 
 def _fused(x: torch.Tensor) -> bool:

@@ -435,9 +435,10 @@ def linear_pair_supported(x1: torch.Tensor, x2: torch.Tensor, n: int) -> bool:
 
 
 @_on_tensor_device
-def linear_pair_forward(x1, x2, weight_cat, col_shift=None, act=None, slope: float = 0.1, out=None, col_scale=None):
-    """act(([x1 | x2] @ weight_cat.T) * col_scale + col_shift) with the two inputs read where they lie
-    (kpreg_linear_pair_forward); weight_cat = [W1 | 0 .. | W2] with W1 padded to a multiple of 32 columns."""
+def linear_pair_forward(x1, x2, weight_cat, col_shift=None, act=None, slope: float = 0.1, out=None, col_scale=None,
+                        post_residual=None, post_act=None):
+    """post_act(act(([x1 | x2] @ weight_cat.T) * col_scale + col_shift) + post_residual) with the two inputs read where they
+    lie (kpreg_linear_pair_forward); weight_cat = [W1 | 0 .. | W2] with W1 padded to a multiple of 32 columns."""
     lib = _lib.load()
     _lib.require_cuda(x1, "x1")
     m, k1 = x1.shape
@@ -452,9 +453,15 @@ def linear_pair_forward(x1, x2, weight_cat, col_shift=None, act=None, slope: flo
     ldc = int(out.stride(0)) if m > 1 else max(int(out.stride(0)), n)
     cs = None if col_scale is None else _f32c(col_scale, "col_scale")
     cb = None if col_shift is None else _f32c(col_shift, "col_shift")
+    pr, ld_post = None, 0
+    if post_residual is not None:
+        pr, ld_post = _rows(post_residual, "post_residual")
+        if pr.shape[0] != m or pr.shape[1] != n:
+            raise RuntimeError("linear_pair: post_residual must be [M, N]")
     rc = lib.kpreg_linear_pair_forward(x1.data_ptr(), int(x1.stride(0)) if m > 1 else k1, k1, x2.data_ptr(),
                                        int(x2.stride(0)) if m > 1 else k2, k2, split.buf.data_ptr(), m, n, _lib.ptr(cs), _lib.ptr(cb),
-                                       ACT[act], float(slope), out.data_ptr(), ldc, _lib.stream_ptr(dev))
+                                       ACT[act], float(slope), _lib.ptr(pr), int(ld_post), ACT[post_act], out.data_ptr(), ldc,
+                                       _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_linear_pair_forward")
     return out
 

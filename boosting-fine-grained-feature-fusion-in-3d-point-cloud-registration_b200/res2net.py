@@ -111,16 +111,26 @@ class my_Bottle2neck(_CacheInvalidating):
         wt, sh = _folded(self.conv1, self.bn1)
         fuse_res = self.downsample is not None and x.shape[1] % 4 == 0
         k_cat = w * n_groups
-        z = torch.empty((x.shape[0], k_cat + (x.shape[1] if fuse_res else 0)), dtype=x.dtype, device=x.device)
         front = (kb.FRONT_KERNEL and gemm == 1 and self.nums == n_groups - 1 and x.dtype == torch.float32 and x.stride(1) == 1
                  and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and ops.front_supported(w, n_groups, x.shape[1]))
         chain = front or (kb.CHAIN_KERNEL and self.nums == n_groups - 1 and ops.chain_supported(w, self.nums))
+        # The front / chain kernels write the copy of x behind the concatenation themselves.  The layer-by-layer path (wide units)
+        # leaves x where it is: conv3 + the residual projection are then ONE GEMM whose reduction runs over z and over x.
+        res_pair = (fuse_res and not chain and gemm == 1 and kb.PAIR_CONV3 and k_cat % 4 == 0
+                    and ops.linear_pair_supported(x, x, self.conv3.weight.shape[0]))
+        z = torch.empty((x.shape[0], k_cat + (x.shape[1] if fuse_res and not res_pair else 0)), dtype=x.dtype, device=x.device)
         if front:
             # conv1 and all chained layers in one tcgen05 kernel: conv1's output never leaves the SM
             ops.front_forward(x, self._front_pack(), z, copy_x=fuse_res)
             t = None
         else:
-            t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm)                  # [N, w * scale]
+            # Layer by layer with w <= 128: conv1 writes its 8 groups straight into z and every chained layer overwrites "its"
+            # group with its output — the pass-through group is then already in place.  Safe because a [128 x w] output tile
+            # of k_gemm_tc covers ALL w columns (tile width 128): a tile's rows are stored after its whole reduction has been
+            # read, and no other tile reads those rows.  (w = 224 spans two column tiles: separate t, one copy of the last group.)
+            in_place = (not chain and gemm == 1 and kb.PAIR_CONV3 and w % 4 == 0 and w <= 128 and self.nums == n_groups - 1
+                        and self.nums > 1)
+            t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm, out=z[:, :k_cat] if in_place else None)  # [N, w * scale]
         if front:
             pass
         elif chain:
@@ -146,18 +156,23 @@ class my_Bottle2neck(_CacheInvalidating):
                                    addend=t[:, (i + 1) * w:(i + 2) * w] if (nxt and not pair) else None, gemm=gemm)
                 if not pair:
                     inp = scratch[i & 1]
-            z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
+            if t.data_ptr() != z.data_ptr():
+                z[:, self.nums * w:k_cat] = t[:, self.nums * w:]
         w3, b3 = _folded(self.conv3, self.bn3)
         if fuse_res:
             # relu(bn3(cat W3^T) + bn_d(x Wd^T)) = relu([cat | x] [W3' | Wd']^T + b3' + bd')
-            if not chain:
+            if not chain and not res_pair:
                 z[:, k_cat:] = x
             wd, bd = _folded(self.downsample[0], self.downsample[1])
-            key = (self.bn3._kpreg_folded[0], self.downsample[1]._kpreg_folded[0])
+            key = (self.bn3._kpreg_folded[0], self.downsample[1]._kpreg_folded[0], res_pair)
             cache = getattr(self, "_kpreg_joint", None)
             if cache is None or cache[0] != key:
-                cache = (key, torch.cat([w3, wd], 1).contiguous(), (b3 + bd).contiguous())
+                pad = (-k_cat) % 32 if res_pair else 0  # the pair GEMM's second operand starts at a multiple of 32 columns
+                cache = (key, torch.cat([w3, w3.new_zeros((w3.shape[0], pad)), wd], 1).contiguous(), (b3 + bd).contiguous())
                 self._kpreg_joint = cache
+            if res_pair:
+                return ops.linear_pair_forward(z, x, cache[1], cache[2], act="relu", post_residual=shortcut,
+                                               post_act="leaky_relu" if shortcut is not None else None)
             return ops.linear_forward(z, cache[1], None, cache[2], act="relu", gemm=gemm, post_residual=shortcut,
                                       post_act="leaky_relu" if shortcut is not None else None)
         residual = x

@@ -203,11 +203,15 @@ KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight,
  * tensor-core GEMM runs over x1 [M, k1] (row pitch ld1) and then over x2 [M, k2] (row pitch ld2).  w_split is the pre-split
  * weight pair (kpreg_split_weights) of Wcat [n_dim, pad32(k1) + k2] = [W1 | zero columns up to a multiple of 32 | W2].
  * With W1 = W2 = W this is (x1 + x2) W^T — one step of my_Bottle2neck's chain (models/backbone_kpconv/res2net.py:141-147)
- * reading the previous group's output and the next group of conv1's output where they lie.  Both bases 16-byte aligned, ld1 and
+ * reading the previous group's output and the next group of conv1's output where they lie; with W1 = conv3, W2 = the residual
+ * projection, x1 = the concatenated group outputs and x2 = the unit's input it is conv3 + downsample of the same unit
+ * (res2net.py:153-159) without a copy of the input behind the concatenation.  post_residual (may be NULL; row pitch ld_post) and
+ * post_act as in kpreg_linear_forward: out = post_act(act(...) + post_residual).  Both bases 16-byte aligned, ld1 and
  * ld2 multiples of 4, k1 >= 4, n_dim >= 8. */
 KPREG_API int kpreg_linear_pair_forward(const float* x1, int ld1, int k1, const float* x2, int ld2, int k2, const float* w_split,
                                         int64_t m_rows, int n_dim, const float* col_scale, const float* col_shift, int act,
-                                        float slope, float* out, int ldc, void* stream);
+                                        float slope, const float* post_residual, int ld_post, int post_act, float* out, int ldc,
+                                        void* stream);
 
 /* Backward of y = x W^T on the tensor cores (3xTF32): dx [M, K] = dy W (may be NULL) and d_weight [N, K] = dy^T x (may be
  * NULL; a split-k reduction over the M rows, accumulated with fp32 atomics).  Returns KPREG_E_INVALID when a shape is not
