@@ -40,6 +40,9 @@ _SIGNATURES = {
     "kpreg_kpconv_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
                                       _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_int, _c_ptr, _c_ptr,
                                       _c_ptr, _c_size, _c_ptr]),
+    "kpreg_kpconv_forward_rowpos": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
+                                             _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
+                                             _c_ptr, _c_size, _c_ptr]),
     "kpreg_kpconv_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64,
                                        _c_i64, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_ptr, _c_ptr,
                                        _c_ptr, _c_ptr, _c_size, _c_ptr]),
@@ -60,6 +63,9 @@ _SIGNATURES = {
     "kpreg_segment_norm_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_segment_norm_forward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
                                             _c_f32, _c_ptr, _c_int, _c_ptr, _c_size, _c_ptr]),
+    "kpreg_segment_norm_rowpos_supported": (_c_int, [_c_int]),
+    "kpreg_segment_norm_forward_rowpos": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int, _c_int,
+                                                   _c_f32, _c_ptr, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "kpreg_segment_norm_backward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_ptr, _c_int, _c_i64, _c_int, _c_f32, _c_ptr, _c_int,
                                              _c_ptr, _c_size, _c_ptr]),
     "kpreg_chain_supported": (_c_int, [_c_int, _c_int]),

@@ -163,7 +163,8 @@ template <int TX>
 __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__ x, int ldx, const int64_t* __restrict__ off,
                                                        int n_clouds, int64_t n_rows, int channels, const double* __restrict__ stats,
                                                        float eps, const float* __restrict__ residual, int ld_res, int act, float slope,
-                                                       float* __restrict__ out, int ldo, int rows_per_cta) {
+                                                       float* __restrict__ out, int ldo, int rows_per_cta,
+                                                       unsigned char* __restrict__ row_pos) {
   constexpr int RY = 256 / TX;
   const int cx = threadIdx.x % TX, ry = threadIdx.x / TX;
   const int ch = blockIdx.y * (4 * TX) + cx * 4;
@@ -199,6 +200,16 @@ __global__ void __launch_bounds__(256) k_segnorm_apply(const float* __restrict__
     y.x = activate(y.x, act, slope); y.y = activate(y.y, act, slope);
     y.z = activate(y.z, act, slope); y.w = activate(y.w, act, slope);
     *reinterpret_cast<float4*>(out + r * ldo + ch) = y;
+    if (row_pos) {
+      // KPConv's normalisation predicate of the row just written (sum of its features > 0, fp64 sum — the arithmetic and
+      // the summation order of k_row_positive_vec): the launcher passes row_pos only when channels == 4 * TX, i.e. the TX
+      // consecutive lanes of this row hold all of it and leave the loop together
+      double s = ((double)y.x + (double)y.y) + ((double)y.z + (double)y.w);
+      const unsigned int grp = (TX == 32 ? 0xffffffffu : ((1u << TX) - 1u)) << ((threadIdx.x & 31) & ~(TX - 1));
+#pragma unroll
+      for (int o = TX / 2; o > 0; o >>= 1) s += __shfl_xor_sync(grp, s, o);
+      if (cx == 0) row_pos[r] = (float)s > 0.0f ? 1 : 0;
+    }
   }
 }
 
@@ -356,6 +367,17 @@ extern "C" int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, si
 extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
                                           int channels, float eps, const float* residual, int ld_res, int act, float slope,
                                           float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream_) {
+  return kpreg_segment_norm_forward_rowpos(x, ldx, lens, n_clouds, n_rows, channels, eps, residual, ld_res, act, slope, out, ldo,
+                                           nullptr, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int kpreg_segment_norm_rowpos_supported(int channels) { return channels == 32 || channels == 64; }
+
+extern "C" int kpreg_segment_norm_forward_rowpos(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
+                                                 int channels, float eps, const float* residual, int ld_res, int act, float slope,
+                                                 float* out, int ldo, unsigned char* row_pos, void* workspace,
+                                                 size_t workspace_bytes, void* stream_) {
+  if (row_pos && !kpreg_segment_norm_rowpos_supported(channels)) return KPREG_E_INVALID;
   if (n_rows < 0 || n_clouds < 1 || channels < 4 || (channels & 3) || (ldx & 3) || (ldo & 3) || act < 0 || act > 2) return KPREG_E_INVALID;
   if (residual && (ld_res & 3)) return KPREG_E_INVALID;
   if (n_rows == 0) return KPREG_OK;
@@ -383,9 +405,9 @@ extern "C" int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t
   else k_segnorm_stats<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, rows);
   KP_LAUNCH_CHECK();
   if (channels <= 32)
-    k_segnorm_apply<8><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows);
+    k_segnorm_apply<8><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows, row_pos);
   else
-    k_segnorm_apply<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows);
+    k_segnorm_apply<16><<<grid, 256, 0, stream>>>(x, ldx, w.off, n_clouds, n_rows, channels, w.stats, eps, residual, ld_res, act, slope, out, ldo, rows, row_pos);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
 }

@@ -1002,6 +1002,15 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
                                     const float* weights, const float* kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
                                     int n_kpts, int c_in, int c_out, float kp_extent, int influence, int aggregation, int gemm,
                                     const int32_t* order, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  return kpreg_kpconv_forward_rowpos(q_pts, s_pts, idx, idx64, x, weights, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, c_out,
+                                     kp_extent, influence, aggregation, gemm, order, nullptr, out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int kpreg_kpconv_forward_rowpos(const float* q_pts, const float* s_pts, const void* idx, int idx64, const float* x,
+                                           const float* weights, const float* kernel_points, int64_t n_q, int64_t n_s, int n_nbrs,
+                                           int n_kpts, int c_in, int c_out, float kp_extent, int influence, int aggregation,
+                                           int gemm, const int32_t* order, const unsigned char* row_pos_in, float* out,
+                                           void* workspace, size_t workspace_bytes, void* stream_) {
   int rc = check_kpconv_args(n_q, n_s, n_nbrs, n_kpts, c_in, c_out, kp_extent, influence, aggregation);
   if (rc) return rc;
   if (n_q == 0) return KPREG_OK;
@@ -1039,14 +1048,15 @@ extern "C" int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, cons
   }
   KpconvWs w = carve_kpconv(workspace, n_q, n_s, n_kpts, c_in, c_out, 0);
   if (w.total > workspace_bytes) return KPREG_E_WORKSPACE;
-  {
+  const unsigned char* row_pos = row_pos_in ? row_pos_in : w.row_pos;
+  if (!row_pos_in) {
     ProfScope prof_rows(KPREG_FAM_GATHER, stream);  // the row pass belongs to the aggregate step
     launch_row_pass(x, n_s, c_in, w.row_pos, stream);
     KP_CUDA_TRY(cudaPeekAtLastError());
   }
-  rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+  rc = idx64 ? launch_gather<int64_t>(q_pts, s_pts, idx, x, row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
                                       influence, aggregation, w.agg, w.inv_num, order, stream)
-             : launch_gather<int32_t>(q_pts, s_pts, idx, x, w.row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
+             : launch_gather<int32_t>(q_pts, s_pts, idx, x, row_pos, kernel_points, n_q, n_s, n_nbrs, n_kpts, c_in, kp_extent,
                                       influence, aggregation, w.agg, w.inv_num, order, stream);
   if (rc) return rc;
   const int kd = n_kpts * c_in;

@@ -147,6 +147,10 @@ class KPConv(ops.CacheInvalidatingModule):
         """``order`` (optional, not in the reference): int32 permutation of the query rows giving a spatially
         coherent processing order (Preprocessor's batch['orders']); it never changes the result."""
         gemm = DEFAULT_GEMM if self.gemm is None else self.gemm
+        if not torch.is_grad_enabled():
+            # inference: no autograd node (x reaches ops.kpconv_forward as the very tensor the norm kernel tagged with its row predicate)
+            return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points, float(self.KP_extent),
+                                      self.KP_influence, self.aggregation_mode, gemm, order)
         return _KPConvFn.apply(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points, float(self.KP_extent),
                                self.KP_influence, self.aggregation_mode, gemm, order)
 
@@ -208,12 +212,13 @@ class BatchNormBlock(nn.Module):
     def reset_parameters(self):
         nn.init.zeros_(self.bias)
 
-    def forward(self, x, stack_lengths, act=None, residual=None):
+    def forward(self, x, stack_lengths, act=None, residual=None, row_pos=False):
         """``act`` / ``residual`` let the fused path apply the activation (and shortcut addition) that
-        follows the norm in the same kernel; the default arguments are the reference's signature."""
+        follows the norm in the same kernel; ``row_pos``: the result feeds a KPConv (ops.segment_norm); the default
+        arguments are the reference's signature."""
         if self.use_bn:
             if _fused(x) and x.shape[1] % 4 == 0:
-                return ops.segment_norm(x, stack_lengths, residual=residual, act=act, slope=0.1)
+                return ops.segment_norm(x, stack_lengths, residual=residual, act=act, slope=0.1, row_pos=row_pos)
             if x.is_cuda and x.shape[1] % 4 == 0 and x.shape[0] > 0:
                 x = _SegNormFn.apply(x, stack_lengths.to(x.device))
             else:
@@ -243,12 +248,13 @@ class UnaryBlock(ops.CacheInvalidatingModule):
         if not no_relu:
             self.leaky_relu = nn.LeakyReLU(0.1)
 
-    def forward(self, x, stack_lengths=None, residual=None, final_act=False):
-        """residual / final_act (fused inference only): leaky_relu(norm(mlp(x)) + residual)."""
+    def forward(self, x, stack_lengths=None, residual=None, final_act=False, feeds_kpconv=False):
+        """residual / final_act (fused inference only): leaky_relu(norm(mlp(x)) + residual); feeds_kpconv: the result is the
+        feature input of a KPConv (its row predicate is then written by the norm kernel)."""
         if _fused(x):
             y = ops.linear_forward(x, self.mlp.weight, gemm=DEFAULT_GEMM)
             act = "leaky_relu" if (final_act or not self.no_relu) else None
-            return self.batch_norm(y, stack_lengths, act=act, residual=residual)
+            return self.batch_norm(y, stack_lengths, act=act, residual=residual, row_pos=feeds_kpconv)
         x = self.batch_norm(ops.linear_train(x, self.mlp), stack_lengths)
         x = x if self.no_relu else self.leaky_relu(x)
         if residual is not None:
@@ -342,7 +348,7 @@ class ResnetBottleneckBlock(nn.Module):
         q_pts, s_pts, inds, lens_post, order = _conv_inputs(batch, self.layer_ind, strided)
         lens_pre = batch['stack_lengths'][self.layer_ind]
 
-        x = self.unary1(features, lens_pre) if isinstance(self.unary1, UnaryBlock) else features
+        x = self.unary1(features, lens_pre, feeds_kpconv=True) if isinstance(self.unary1, UnaryBlock) else features
         x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)
         if _fused(x) and not isinstance(self.unary_shortcut, UnaryBlock):
             # identity shortcut: leaky_relu(res2net(x) + shortcut) rides on res2net's last GEMM

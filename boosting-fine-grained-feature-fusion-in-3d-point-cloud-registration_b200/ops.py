@@ -184,6 +184,7 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
         raise ValueError("Unknown influence function type (config.KP_influence)")
     if aggregation not in AGGREGATION:
         raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    row_pos = row_predicate_of(x)  # written by the segment norm that produced x (inference), or None
     q_pts, s_pts, x = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
     weights_in = weights
     weights, kernel_points = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
@@ -192,6 +193,8 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     k, c_in, c_out = weights.shape
     if x.shape[0] != n_s or x.shape[1] != c_in or idx.shape[0] != n_q or kernel_points.shape[0] != k:
         raise RuntimeError("KPConv: inconsistent shapes")
+    if row_pos is not None and (row_pos[1] != x.data_ptr() or row_pos[0].shape[0] != n_s or row_pos[0].device != x.device):
+        row_pos = None
     dev = q_pts.device
     out = torch.empty((n_q, c_out), dtype=torch.float32, device=dev)
     nbytes = _lib.size_query("kpreg_kpconv_workspace_bytes", n_q, n_s, k, c_in, c_out, 0)
@@ -199,12 +202,22 @@ def kpconv_forward(q_pts, s_pts, idx, x, weights, kernel_points, kp_extent: floa
     w_ptr = weights.data_ptr()
     if gemm == 1 and not torch.is_grad_enabled() and (k * c_in) % 4 == 0 and k * c_in >= 4 and c_out >= 8 and n_q > 0:
         w_ptr, gemm = cached_split(weights_in, True).buf.data_ptr(), 2  # inference: the weights were split once
-    rc = lib.kpreg_kpconv_forward(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
-                                  w_ptr, kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
-                                  float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation], int(gemm),
-                                  _order_ptr(order, n_q), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    rc = lib.kpreg_kpconv_forward_rowpos(q_pts.data_ptr(), s_pts.data_ptr(), idx.data_ptr(), idx64, x.data_ptr(),
+                                         w_ptr, kernel_points.data_ptr(), n_q, n_s, h, k, c_in, c_out,
+                                         float(kp_extent), INFLUENCE[influence], AGGREGATION[aggregation], int(gemm),
+                                         _order_ptr(order, n_q), None if row_pos is None else row_pos[0].data_ptr(),
+                                         out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_kpconv_forward")
     return out
+
+
+def row_predicate_of(x):
+    """(flags uint8 [N], data_ptr) attached by segment_norm(..., row_pos=True) to its output, if ``x`` is that very tensor
+    and has not been written since (version counter); None otherwise."""
+    tag = getattr(x, "_kpreg_row_pos", None)
+    if tag is None or tag[2] != x._version:
+        return None
+    return tag[0], tag[1]
 
 
 @_on_tensor_device
@@ -521,8 +534,10 @@ def linear_train(x: torch.Tensor, linear: torch.nn.Linear) -> torch.Tensor:
 
 
 @_on_tensor_device
-def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: float = 1e-5, out=None):
-    """Per-cloud, per-channel (x - mean) * rstd (+ residual) (+ activation) (kpreg_segment_norm_forward)."""
+def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: float = 1e-5, out=None, row_pos: bool = False):
+    """Per-cloud, per-channel (x - mean) * rstd (+ residual) (+ activation) (kpreg_segment_norm_forward).
+    ``row_pos``: the output feeds a KPConv — where the kernel can (32 / 64 channels) it also writes that KPConv's row
+    predicate (feature sum > 0) and tags the output with it, which saves kpconv_forward its own pass over the features."""
     lib = _lib.load()
     x, ldx = _rows(x, "x")
     lens = _i32c(lens, "stack_lengths")
@@ -536,10 +551,16 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
         res_ptr = residual.data_ptr()
     nbytes = _lib.size_query("kpreg_segment_norm_workspace_bytes", int(lens.shape[0]), c)
     ws = _lib.workspaces.get(nbytes, dev)
-    rc = lib.kpreg_segment_norm_forward(x.data_ptr(), ldx, lens.data_ptr(), int(lens.shape[0]), n, c, float(eps), res_ptr,
-                                        ld_res, ACT[act], float(slope), out.data_ptr(), int(out.stride(0)) if n > 1 else c,
-                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    flags = None
+    if row_pos and n > 0 and out.is_contiguous() and lib.kpreg_segment_norm_rowpos_supported(c):
+        flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+    rc = lib.kpreg_segment_norm_forward_rowpos(x.data_ptr(), ldx, lens.data_ptr(), int(lens.shape[0]), n, c, float(eps), res_ptr,
+                                               ld_res, ACT[act], float(slope), out.data_ptr(), int(out.stride(0)) if n > 1 else c,
+                                               None if flags is None else flags.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               _lib.stream_ptr(dev))
     _lib.check(rc, "kpreg_segment_norm_forward")
+    if flags is not None:
+        out._kpreg_row_pos = (flags, out.data_ptr(), out._version)
     return out
 
 

@@ -134,6 +134,14 @@ KPREG_API int kpreg_kpconv_forward(const float* q_pts, const float* s_pts, const
                          int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out,
                          float kp_extent, int influence, int aggregation, int gemm, const int32_t* order,
                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with the normalisation's row predicate supplied by the caller: row_pos [n_s] bytes, row_pos[j] != 0 iff the feature
+ * sum of support row j is positive (finegrained_kpconv_blocks.py:396-397) — kpreg_segment_norm_forward_rowpos writes it
+ * while it writes x, which saves this call's own pass over x.  row_pos == NULL: identical to kpreg_kpconv_forward. */
+KPREG_API int kpreg_kpconv_forward_rowpos(const float* q_pts, const float* s_pts, const void* idx, int idx64,
+                         const float* x, const float* weights, const float* kernel_points,
+                         int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts, int c_in, int c_out,
+                         float kp_extent, int influence, int aggregation, int gemm, const int32_t* order,
+                         const unsigned char* row_pos, float* out, void* workspace, size_t workspace_bytes, void* stream);
 KPREG_API int kpreg_kpconv_backward(const float* q_pts, const float* s_pts, const void* idx, int idx64,
                           const float* x, const float* weights, const float* kernel_points,
                           const float* grad_out, int64_t n_q, int64_t n_s, int n_nbrs, int n_kpts,
@@ -224,6 +232,14 @@ KPREG_API int kpreg_segment_norm_workspace_bytes(int n_clouds, int channels, siz
 KPREG_API int kpreg_segment_norm_forward(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
                                          int channels, float eps, const float* residual, int ld_res, int act, float slope,
                                          float* out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* The same, also writing KPConv's row predicate of the output (row_pos [n_rows] bytes: 1 iff the fp64 sum of out's row is
+ * positive; NULL = none) for the KPConv that consumes `out` (kpreg_kpconv_forward_rowpos).  Only where one thread group holds
+ * a whole row: kpreg_segment_norm_rowpos_supported(channels) != 0 (32 or 64 channels), KPREG_E_INVALID otherwise. */
+KPREG_API int kpreg_segment_norm_rowpos_supported(int channels);
+KPREG_API int kpreg_segment_norm_forward_rowpos(const float* x, int ldx, const int32_t* lens, int n_clouds, int64_t n_rows,
+                                                int channels, float eps, const float* residual, int ld_res, int act, float slope,
+                                                float* out, int ldo, unsigned char* row_pos, void* workspace,
+                                                size_t workspace_bytes, void* stream);
 /* Backward of the plain norm (no residual / activation): dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) per cloud and
  * channel, statistics recomputed from x.  Same workspace size as the forward. */
 KPREG_API int kpreg_segment_norm_backward(const float* x, int ldx, const float* dy, int ld_dy, const int32_t* lens,

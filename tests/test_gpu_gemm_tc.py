@@ -90,6 +90,46 @@ def test_segment_norm_matches_instance_norm(lens, c):
     assert rel_err(got2.cpu().numpy(), want2.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("lens,c", [([37, 1200, 5, 3001], 32), ([20000, 21000, 1, 300], 64), ([700, 650], 128)])
+def test_segment_norm_row_predicate_feeds_kpconv(lens, c):
+    """segment_norm(..., row_pos=True): where the kernel supports it (32 / 64 channels) the output carries KPConv's row
+    predicate (sum of the row's features > 0, finegrained_kpconv_blocks.py:396-397) — equal to the definition evaluated on the
+    output, identical values with and without it, dropped once the tensor is written to — and kpconv_forward gives the same
+    result with the tag as with its own pass over the features."""
+    torch.manual_seed(c + 1)
+    lens_t = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    n = sum(lens)
+    x = torch.randn(n, c, device="cuda") * 2 + 0.05
+    plain = ops.segment_norm(x, lens_t, act="leaky_relu", slope=0.1)
+    tagged = ops.segment_norm(x, lens_t, act="leaky_relu", slope=0.1, row_pos=True)
+    assert torch.equal(plain, tagged)
+    tag = ops.row_predicate_of(tagged)
+    assert ops.row_predicate_of(plain) is None
+    if c > 64:
+        assert tag is None
+        return
+    flags, ptr = tag
+    assert ptr == tagged.data_ptr() and flags.dtype == torch.uint8 and flags.shape == (n,)
+    want = tagged.double().sum(1).float() > 0
+    assert torch.equal(flags.bool(), want)
+    raw = ops.segment_norm(x, lens_t, row_pos=True)  # no activation: row sums of either sign
+    want_raw = raw.double().sum(1).float() > 0
+    assert torch.equal(ops.row_predicate_of(raw)[0].bool(), want_raw)
+    assert 0.2 < want_raw.float().mean().item() < 0.8
+    # the KPConv that consumes it
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    pts = torch.rand((n, 3), device="cuda", generator=gen)
+    idx = torch.randint(0, n + 40, (n, 12), device="cuda", generator=gen).clamp(max=n).to(torch.int32)  # some shadow entries
+    weights = torch.randn((15, c, 16), device="cuda", generator=gen) / c ** 0.5
+    kp = torch.rand((15, 3), device="cuda", generator=gen) * 0.2 - 0.1
+    with torch.no_grad():
+        a = ops.kpconv_forward(pts, pts, idx, tagged, weights, kp, 0.15, gemm=1)
+        b = ops.kpconv_forward(pts, pts, idx, tagged.clone(), weights, kp, 0.15, gemm=1)
+    assert torch.equal(a, b)
+    tagged.add_(1.0)                       # written to: the tag no longer describes the tensor
+    assert ops.row_predicate_of(tagged) is None
+
+
 @pytest.mark.parametrize("w,n_layers,m,c_x", [(28, 7, 5000, 32), (56, 7, 3001, 64), (14, 7, 257, 16), (16, 3, 31, 0), (64, 5, 700, 30),
                                               (56, 7, 256, 0)])
 def test_chain_kernel_matches_layerwise_reference(w, n_layers, m, c_x):
