@@ -543,6 +543,7 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
     lens = _i32c(lens, "stack_lengths")
     n, c = x.shape
     dev = x.device
+    own_out = out is None  # only a tensor allocated here is tagged: nothing else can write it behind the version counter
     if out is None:
         out = torch.empty((n, c), dtype=torch.float32, device=dev)
     res_ptr, ld_res = None, 0
@@ -552,7 +553,7 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
     nbytes = _lib.size_query("kpreg_segment_norm_workspace_bytes", int(lens.shape[0]), c)
     ws = _lib.workspaces.get(nbytes, dev)
     flags = None
-    if row_pos and n > 0 and out.is_contiguous() and lib.kpreg_segment_norm_rowpos_supported(c):
+    if row_pos and own_out and n > 0 and lib.kpreg_segment_norm_rowpos_supported(c):
         flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     rc = lib.kpreg_segment_norm_forward_rowpos(x.data_ptr(), ldx, lens.data_ptr(), int(lens.shape[0]), n, c, float(eps), res_ptr,
                                                ld_res, ACT[act], float(slope), out.data_ptr(), int(out.stride(0)) if n > 1 else c,
