@@ -19,6 +19,8 @@ import logging
 from typing import List
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -137,6 +139,19 @@ class Preprocessor(nn.Module):
                 grid = ops.CellGrid(points, lens, cell) if cell > 0 else None
             order = grid.order if grid is not None else None
 
+            sub = counts = counts_host = counts_ready = None
+            if strided:
+                # The subsample goes first and its sizes start their way to the host at once (pinned buffer + event): the radius
+                # queries enqueued behind it do not depend on them, so the host learns the next level's size while the GPU is
+                # still busy and the one unavoidable read-back per level no longer drains the stream.
+                dl = 2 * r_normal / cfg.conv_radius
+                sub, counts = ops.subsample(points, lens, dl)
+                if counts.is_cuda and os.environ.get("KPREG_SYNC_COUNTS", "")[:1] != "1":  # (=1: blocking read-back, A/B measurements)
+                    counts_host = torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True)
+                    counts_host.copy_(counts, non_blocking=True)
+                    counts_ready = torch.cuda.Event()
+                    counts_ready.record(torch.cuda.current_stream(counts.device))
+
             if pending_up is not None:
                 up_tabs.append(query(grid, pending_up[0], pending_up[1], pending_up[2], pending_up[3], pending_up[4]))
                 pending_up = None
@@ -153,9 +168,11 @@ class Preprocessor(nn.Module):
                 first_table[0] = self._finish(conv_tabs[0], int(st0[0]), dev)
                 yield {'points': [points], 'neighbors': [first_table[0]], 'stack_lengths': [lens], 'orders': [order]}
             if strided:
-                dl = 2 * r_normal / cfg.conv_radius
-                sub, counts = ops.subsample(points, lens, dl)
-                host = counts.cpu()  # sizes of the next level: the one unavoidable read-back per level
+                if counts_ready is not None:
+                    counts_ready.synchronize()
+                    host = counts_host
+                else:
+                    host = counts.cpu()
                 if int(host[-1]) != 0:
                     raise RuntimeError("Preprocessor: voxel grid too large to index")
                 m = int(host[-2])
