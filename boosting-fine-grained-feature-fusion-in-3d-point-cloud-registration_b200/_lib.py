@@ -58,6 +58,7 @@ _SIGNATURES = {
     "kpreg_linear_backward_workspace_bytes": (_c_int, [_c_i64, _c_int, _c_int, ctypes.POINTER(_c_size)]),
     "kpreg_linear_backward": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_int, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_int, _c_ptr, _c_ptr,
                                        _c_size, _c_ptr]),
+    "kpreg_linear_tile_cols": (_c_int, [_c_int, _c_int]),
     "kpreg_linear_pair_forward": (_c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_int, _c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_int,
                                            _c_f32, _c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_ptr]),
     "kpreg_segment_norm_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),

@@ -25,6 +25,7 @@ int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int ld
 int kpconv_gemm_tc_prepare_weights(const float* weights, int kd, int n, int transpose, float* w_split, cudaStream_t stream);
 size_t kpconv_gemm_tc_weight_bytes(int kd, int n);
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a);
+int gemm_tc_block_n(int kd, int n);
 int launch_gemm_tn(const float* a, int lda, const float* b, int ldb, const float* row_scale, float* c, int ldc, int64_t k_rows,
                    int ma_dim, int nb_dim, int c_transposed, void* split_ws, cudaStream_t stream);
 size_t gemm_tn_workspace_bytes(int64_t k_rows, int nb_dim);
@@ -291,6 +292,11 @@ using namespace kpreg;
 
 extern "C" int kpreg_gemm_supported(int64_t m_rows, int k_dim, int n_dim, int ldx, const void* x) {
   return gemm_tc_supported(m_rows, k_dim, n_dim, ldx, x) ? 1 : 0;
+}
+
+extern "C" int kpreg_linear_tile_cols(int k_dim, int n_dim) {
+  if (k_dim < 1 || n_dim < 1) return 0;
+  return gemm_tc_block_n(k_dim, n_dim);
 }
 
 extern "C" int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes) {

@@ -682,6 +682,22 @@ size_t kpconv_gemm_tc_weight_bytes(int kd, int n) {
   return align_up((size_t)2 * (size_t)npad_for(n) * (size_t)ldb_for(kd) * sizeof(float) + 512, 256);
 }
 
+// Tile width (output columns per CTA tile) the tensor-core GEMM uses for a [*, kd] x [kd, n] product.
+int gemm_tc_block_n(int kd, int n) {
+  const bool h2 = gemm_h2();
+  const int num_hi = kd > 1024 ? 3 : 1;
+  // wide outputs of long reductions: 128-column tiles with single-buffered accumulators (4 x 128 TMEM columns)
+  static const bool no_wide3 = [] { const char* e = getenv("KPREG_GEMM_NO_WIDE3"); return e && e[0] == '1'; }();
+  const bool wide3 = num_hi == 3 && n > 64 && !no_wide3;
+  // fp16 split, K <= 1024, wide outputs: 128 x 256 tiles (two single-buffered 256-column accumulators fill TMEM) — the
+  // mainloop is bound by shared-memory bandwidth and a 256-column MMA reads A once for twice the output.  Outputs of
+  // 129 .. 255 columns (res2net's w = 224 chain layers) take ONE 256-column tile rather than a 128 + remainder pair: A is
+  // read once, and a single column tile is what lets the chained layers work in place (res2net.py).
+  static const bool no_n256 = [] { const char* e = getenv("KPREG_GEMM_NO_N256"); return e && e[0] == '1'; }();
+  const bool n256 = h2 && num_hi == 1 && n > 128 && kd >= 192 && !no_n256;
+  return n256 ? 256 : (n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128));
+}
+
 bool gemm_tc_supported(int64_t m, int kd, int n, int lda, const void* a) {
   return m > 0 && kd >= 4 && (lda % 4) == 0 && n >= 8 && (reinterpret_cast<uintptr_t>(a) % 16) == 0;
 }
@@ -739,14 +755,7 @@ int launch_gemm_tc_pair(const float* a, int lda, int k1, const float* a2, int ld
   const float* lo = w_split + (size_t)npad_for(n) * ldb;
   // long reductions rotate the hi*hi products over three accumulators (see the accuracy note above)
   const int num_hi = kd > 1024 ? 3 : 1;
-  // wide outputs of long reductions: 128-column tiles with single-buffered accumulators (4 x 128 TMEM columns)
-  static const bool no_wide3 = [] { const char* e = getenv("KPREG_GEMM_NO_WIDE3"); return e && e[0] == '1'; }();
-  const bool wide3 = num_hi == 3 && n > 64 && !no_wide3;
-  // fp16 split, K <= 1024, wide outputs: 128 x 256 tiles (two single-buffered 256-column accumulators fill TMEM) — the
-  // mainloop is bound by shared-memory bandwidth and a 256-column MMA reads A once for twice the output
-  static const bool no_n256 = [] { const char* e = getenv("KPREG_GEMM_NO_N256"); return e && e[0] == '1'; }();
-  const bool n256 = h2 && num_hi == 1 && n >= 256 && kd >= 256 && !no_n256;
-  const int block_n = n256 ? 256 : (n <= 32 ? 32 : ((n <= 64 || (num_hi == 3 && !wide3)) ? 64 : 128));
+  const int block_n = gemm_tc_block_n(kd, n);
   CUtensorMap ma, ma2, mbh, mbl;
   int rc = make_map(&ma, a, m, a2 ? k1 : kd, lda, BLOCK_M);
   if (rc) return rc;

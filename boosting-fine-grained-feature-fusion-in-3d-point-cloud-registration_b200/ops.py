@@ -438,6 +438,11 @@ def pair_weight(weight: torch.Tensor) -> torch.Tensor:
     return torch.cat([weight, weight.new_zeros((n, pad)), weight], 1).contiguous()
 
 
+def linear_tile_cols(k: int, n: int) -> int:
+    """Output columns per CTA tile of the tensor-core GEMM for a [*, k] x [k, n] product (kpreg_linear_tile_cols)."""
+    return int(_lib.load().kpreg_linear_tile_cols(int(k), int(n)))
+
+
 def linear_pair_supported(x1: torch.Tensor, x2: torch.Tensor, n: int) -> bool:
     """The TMA addressing rule of kpreg_linear_pair_forward: fp32 row slices, 16-byte aligned bases and row pitches."""
     ok = True

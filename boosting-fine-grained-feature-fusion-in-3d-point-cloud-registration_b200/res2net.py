@@ -124,12 +124,13 @@ class my_Bottle2neck(_CacheInvalidating):
             ops.front_forward(x, self._front_pack(), z, copy_x=fuse_res)
             t = None
         else:
-            # Layer by layer with w <= 128: conv1 writes its 8 groups straight into z and every chained layer overwrites "its"
-            # group with its output — the pass-through group is then already in place.  Safe because a [128 x w] output tile
-            # of k_gemm_tc covers ALL w columns (tile width 128): a tile's rows are stored after its whole reduction has been
-            # read, and no other tile reads those rows.  (w = 224 spans two column tiles: separate t, one copy of the last group.)
-            in_place = (not chain and gemm == 1 and kb.PAIR_CONV3 and w % 4 == 0 and w <= 128 and self.nums == n_groups - 1
-                        and self.nums > 1)
+            # Layer by layer: conv1 writes its 8 groups straight into z and every chained layer overwrites "its" group with
+            # its output — the pass-through group is then already in place.  Safe where ONE output tile of k_gemm_tc covers
+            # all w columns (kpreg_linear_tile_cols: 128 at w = 112, 256 at w = 224 with the fp16 split): a tile's rows are
+            # stored after its whole reduction has been read, and no other tile reads those rows.  Otherwise: separate t and
+            # one copy of the last group.
+            in_place = (not chain and gemm == 1 and kb.PAIR_CONV3 and w % 4 == 0 and self.nums == n_groups - 1 and self.nums > 1
+                        and w <= min(ops.linear_tile_cols(w, w), ops.linear_tile_cols((w + 31) // 32 * 32 + w, w)))
             t = ops.linear_forward(x, wt, None, sh, act="relu", gemm=gemm, out=z[:, :k_cat] if in_place else None)  # [N, w * scale]
         if front:
             pass

@@ -202,6 +202,10 @@ KPREG_API int kpreg_split_weights(const float* weight, int k_dim, int n_dim, int
                                   void* stream);
 KPREG_API int kpreg_gemm_supported(int64_t m_rows, int k_dim, int n_dim, int ldx, const void* x);
 KPREG_API int kpreg_linear_workspace_bytes(int k_dim, int n_dim, size_t* bytes);
+/* Output columns per CTA tile of the tensor-core GEMM for a [*, k_dim] x [k_dim, n_dim] product (32 / 64 / 128 / 256).  When
+ * n_dim <= this width, a tile's rows are stored only after its whole reduction has been read and no other tile reads them:
+ * `out` may then overlap columns of `x` (res2net's chained layers overwrite conv1's groups in place). */
+KPREG_API int kpreg_linear_tile_cols(int k_dim, int n_dim);
 KPREG_API int kpreg_linear_forward(const float* x, int ldx, const float* weight, int64_t m_rows, int k_dim, int n_dim,
                                    const float* col_scale, const float* col_shift, const float* residual, int ld_res,
                                    int act, float slope, float* out, int ldc, float* out2, int ld2, const float* addend,
