@@ -40,6 +40,7 @@ CHAIN_KERNEL = True
 import os as _os
 # (the front kernel always splits operands into fp16 pairs: under KPREG_GEMM_TF32=1 — fp32 range — it is not used)
 FRONT_KERNEL = _os.environ.get("KPREG_NO_FRONT", "")[:1] != "1" and _os.environ.get("KPREG_GEMM_TF32", "")[:1] != "1"
+SHARED_UNARY = _os.environ.get("KPREG_NO_SHARED_UNARY", "")[:1] != "1"  # unary1 and the shortcut's unary of a block as ONE GEMM over the block input
 PAIR_CONV3 = _os.environ.get("KPREG_NO_PAIR_CONV3", "")[:1] != "1"  # wide res2net units: conv3 + residual projection over (z, x) without copying x
 
 
@@ -343,10 +344,32 @@ class ResnetBottleneckBlock(nn.Module):
                                if in_dim != out_dim else nn.Identity())
         self.leaky_relu = nn.LeakyReLU(0.1)
 
+    def _joint_unary_weight(self):
+        """[W_unary1 ; W_shortcut] ([mid + out, in]): both Linear layers read the block input, one GEMM reads it once."""
+        w1, w2 = self.unary1.mlp.weight, self.unary_shortcut.mlp.weight
+        key = (w1._version, w2._version, w1.data_ptr(), w2.data_ptr(), ops.cache_epoch())
+        cache = getattr(self, "_kpreg_joint_unary", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                cache = (key, torch.cat([w1, w2], 0).contiguous())
+            self._kpreg_joint_unary = cache
+        return cache[1]
+
     def forward(self, features, batch):
         strided = 'strided' in self.block_name
         q_pts, s_pts, inds, lens_post, order = _conv_inputs(batch, self.layer_ind, strided)
         lens_pre = batch['stack_lengths'][self.layer_ind]
+
+        if (SHARED_UNARY and not strided and _fused(features) and self.use_bn and isinstance(self.unary1, UnaryBlock)
+                and isinstance(self.unary_shortcut, UnaryBlock) and self.unary1.out_dim % 4 == 0 and features.shape[0] > 0):
+            # inference, shortcut through a unary: y = features [W1 ; Ws]^T in one GEMM (the block input crosses HBM once), then
+            # the two norms on column slices of y — the arithmetic of every output column is that of the separate layers
+            mid = self.unary1.out_dim
+            y = ops.linear_forward(features, self._joint_unary_weight(), gemm=DEFAULT_GEMM)
+            x = self.unary1.batch_norm(y[:, :mid], lens_pre, act="leaky_relu", row_pos=True)
+            x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)
+            x = self.res2net(x)
+            return self.unary_shortcut.batch_norm(y[:, mid:], lens_post, act="leaky_relu", residual=x)
 
         x = self.unary1(features, lens_pre, feeds_kpconv=True) if isinstance(self.unary1, UnaryBlock) else features
         x = self.batch_norm_conv(self.KPConv(q_pts, s_pts, inds, x, order), lens_post)

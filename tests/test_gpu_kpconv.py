@@ -297,7 +297,7 @@ def test_encoder_fused_path_matches_reference_r2_fixture(golden_encoder_r2, pref
     assert err < TOL and max(errs) < TOL
 
 
-@pytest.mark.parametrize("variant", ["no_front", "no_front_no_pair", "no_front_no_chain", "no_pair_conv3"])
+@pytest.mark.parametrize("variant", ["no_front", "no_front_no_pair", "no_front_no_chain", "no_pair_conv3", "no_shared_unary"])
 def test_encoder_fallback_paths_match_reference_r2_fixture(golden_encoder_r2, variant, monkeypatch):
     """The slower routes of the fused res2net unit — conv1 as its own GEMM + the mma.sync chain kernel (no front kernel), the
     side-output chain scheme (no pair GEMM) and layer-by-layer chains at every width (no chain kernel) — against the same
@@ -306,7 +306,10 @@ def test_encoder_fallback_paths_match_reference_r2_fixture(golden_encoder_r2, va
     from test_oracle import r2_case, r2_state_dict
     g = golden_encoder_r2
     cfg, d_bottle, clouds = r2_case(g, "tdm")
-    if variant == "no_pair_conv3":
+    if variant == "no_shared_unary":
+        # unary1 and the shortcut's unary as two GEMMs over the block input
+        monkeypatch.setattr(kb, "SHARED_UNARY", False)
+    elif variant == "no_pair_conv3":
         # wide units as before: x copied behind the concatenation, conv1's output in its own buffer, last group copied into z
         monkeypatch.setattr(kb, "PAIR_CONV3", False)
     else:
