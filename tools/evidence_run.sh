@@ -1,8 +1,8 @@
 # One gpurun call that refreshes the evidence under gpurun_out/ (copied to profiles/ by hand): tests, bench line, layer times,
 # ncu launch list + DRAM bytes of one 8-pair step, --set full of the aggregate kernel, reference arm.
 set -x
-python -m pytest tests -m gpu -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python -m pytest tests -m gpu -q 2>&1 | tail -2 | tee gpurun_out/r3_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2 | tee gpurun_out/r3_smoke.txt
 python bench.py > gpurun_out/r3_bench_n1.json 2> gpurun_out/r3_bench_n1.err
 python tools/bench_layers.py 64 3 > gpurun_out/r3_layer_times.txt 2>&1
 KPREG_BENCH_NO_RAMP=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
