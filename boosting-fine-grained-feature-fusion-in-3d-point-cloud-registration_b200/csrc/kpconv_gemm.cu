@@ -172,6 +172,10 @@ __global__ void __launch_bounds__(gemm_threads(BLOCK_N, AT), 1) k_gemm_tc(const 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (descriptor prefetch, barrier init, TMEM allocation) touches no data of the
+  // kernel in front of this one on the stream and may run while that kernel's last CTAs drain; every global access is below.
+  // (A no-op when the launch does not carry the attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ---------------- TMA producer
@@ -666,6 +670,23 @@ int launch_tile_config(const CUtensorMap& ma, const CUtensorMap& ma2, int kb_spl
   const int64_t tiles = (int64_t)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   if (tiles >= ((int64_t)1 << 31) || M >= ((int64_t)1 << 31)) return KPREG_E_RANGE;  // 32-bit tile / row arithmetic in the kernel
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  static const bool pdl = [] { const char* e = getenv("KPREG_GEMM_PDL"); return e && e[0] == '1'; }();
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)gemm_threads(BLOCK_N, AT));
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_i = N, k_i = K, ldc_i = ldc;
+    KP_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT>, ma, ma2, kb_split, mbh, mbl, mc, mo2, C, M, n_i, k_i,
+                                   ldc_i, ep));
+    return KPREG_OK;
+  }
   k_gemm_tc<BLOCK_N, NUM_HI, STAGES, ACC_BUFS, H2, AT><<<grid, gemm_threads(BLOCK_N, AT), L::kTotal, stream>>>(ma, ma2, kb_split, mbh, mbl, mc, mo2, C, M, N, K, ldc, ep);
   KP_LAUNCH_CHECK();
   return KPREG_OK;
