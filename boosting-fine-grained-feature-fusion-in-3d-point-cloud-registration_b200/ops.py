@@ -215,7 +215,7 @@ def row_predicate_of(x):
     """(flags uint8 [N], data_ptr) attached by segment_norm(..., row_pos=True) to its output, if ``x`` is that very tensor
     and has not been written since (version counter); None otherwise."""
     tag = getattr(x, "_kpreg_row_pos", None)
-    if tag is None or tag[2] != x._version:
+    if tag is None or x.is_inference() or tag[2] != x._version:
         return None
     return tag[0], tag[1]
 
@@ -558,7 +558,8 @@ def segment_norm(x, lens, residual=None, act=None, slope: float = 0.1, eps: floa
     nbytes = _lib.size_query("kpreg_segment_norm_workspace_bytes", int(lens.shape[0]), c)
     ws = _lib.workspaces.get(nbytes, dev)
     flags = None
-    if row_pos and own_out and n > 0 and lib.kpreg_segment_norm_rowpos_supported(c):
+    # (tensors created under torch.inference_mode() have no version counter: not tagged, KPConv runs its own row pass)
+    if row_pos and own_out and n > 0 and not out.is_inference() and lib.kpreg_segment_norm_rowpos_supported(c):
         flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     rc = lib.kpreg_segment_norm_forward_rowpos(x.data_ptr(), ldx, lens.data_ptr(), int(lens.shape[0]), n, c, float(eps), res_ptr,
                                                ld_res, ACT[act], float(slope), out.data_ptr(), int(out.stride(0)) if n > 1 else c,

@@ -128,6 +128,11 @@ def test_segment_norm_row_predicate_feeds_kpconv(lens, c):
     assert torch.equal(a, b)
     tagged.add_(1.0)                       # written to: the tag no longer describes the tensor
     assert ops.row_predicate_of(tagged) is None
+    with torch.inference_mode():           # inference tensors carry no version counter: never tagged, same values
+        inf = ops.segment_norm(x, lens_t, act="leaky_relu", slope=0.1, row_pos=True)
+        assert ops.row_predicate_of(inf) is None and torch.equal(inf, plain)
+        c_inf = ops.kpconv_forward(pts, pts, idx, inf, weights, kp, 0.15, gemm=1)
+    assert torch.equal(c_inf, a)
 
 
 @pytest.mark.parametrize("w,n_layers,m,c_x", [(28, 7, 5000, 32), (56, 7, 3001, 64), (14, 7, 257, 16), (16, 3, 31, 0), (64, 5, 700, 30),
