@@ -1,5 +1,9 @@
-import os, sys
-ROOT = "/root/repo"
+"""Development aid: which PyTorch ops (copies, casts, element-wise kernels) are left in one step of the path, grouped by input
+shape with the Python stack that issued them — how the strided copies of the wide res2net units were found."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from torch.profiler import ProfilerActivity, profile
