@@ -58,6 +58,22 @@ def test_size_queries_work_without_gpu():
     assert _lib.size_query("kpreg_kpconv_workspace_bytes", 1000, 1000, 15, 32, 32, 0) >= 1000 * 15 * 32 * 4
 
 
+def test_tile_width_and_row_predicate_queries_without_gpu():
+    """kpreg_linear_tile_cols / kpreg_segment_norm_rowpos_supported are pure host functions.  The in-place chain of the wide
+    res2net units (res2net.py) relies on ONE output tile covering a whole group: w = 112 -> 128 columns, w = 224 -> 256 columns
+    (fp16 split) for both the first layer (K = w) and the pair layers (K = pad32(w) + w)."""
+    _ensure_built()
+    lib = _lib.load()
+    assert lib.kpreg_linear_tile_cols(64, 32) == 32 and lib.kpreg_linear_tile_cols(128, 64) == 64
+    assert lib.kpreg_linear_tile_cols(112, 112) == 128 and lib.kpreg_linear_tile_cols(128 + 112, 112) == 128
+    if os.environ.get("KPREG_GEMM_TF32", "")[:1] != "1" and os.environ.get("KPREG_GEMM_NO_N256", "")[:1] != "1":
+        assert lib.kpreg_linear_tile_cols(224, 224) == 256 and lib.kpreg_linear_tile_cols(224 + 224, 224) == 256
+        assert lib.kpreg_linear_tile_cols(512, 256) == 256
+    assert lib.kpreg_linear_tile_cols(2048, 1024) == 128     # long reductions: 128-column tiles
+    assert lib.kpreg_linear_tile_cols(0, 8) == 0
+    assert [bool(lib.kpreg_segment_norm_rowpos_supported(c)) for c in (16, 32, 64, 128, 256)] == [False, True, True, False, False]
+
+
 def test_chain_kernel_support_matrix_without_gpu():
     """kpreg_chain_supported / kpreg_chain_pack_bytes are pure host functions: the res2net widths of the shipped configs
     (w = floor(C * 14 / 64) for C = 64 .. 1024, 7 chained layers) map to the register-resident kernel up to w = 56."""
